@@ -1,0 +1,62 @@
+"""CPU checks of the drop-in boundary: the library builds, loads, exports every symbol declared in
+include/transfer_em_b200.h, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "transfer_em_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tem_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from transfer_em_b200 import build, _lib
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == set(names), set(_lib.EXPORTED_SYMBOLS) ^ set(names)
+    assert _lib.load().tem_abi_version() == _lib.ABI_VERSION
+
+
+def test_config_struct_layout_matches_header():
+    from transfer_em_b200 import _lib
+    cfg = _lib.TemConfig()
+    _lib.load().tem_default_config(ctypes.byref(cfg))
+    assert (cfg.abi_version, cfg.is3d, cfg.wf, cfg.dimsize, cfg.dropout, cfg.train) == (1, 1, 8, 74, 1, 1)
+    assert abs(cfg.lr - 2e-4) < 1e-9 and abs(cfg.beta1 - 0.5) < 1e-9 and abs(cfg.eps - 1e-7) < 1e-12     # cgan.py:69-73
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    from transfer_em_b200 import EM2EM, _lib
+    with pytest.raises(_lib.TemError):
+        EM2EM(74, "nogpu")
+
+
+def test_reference_argument_validation_without_gpu():
+    from transfer_em_b200 import EM2EM, unet_generator
+    with pytest.raises(RuntimeError):
+        EM2EM(64, "x")                    # cgan.py:52-53
+    with pytest.raises(RuntimeError):
+        unet_generator(76)                # generator.py:37-38
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under transfer_em_b200/ may import or execute it."""
+    pk = os.path.join(ROOT, "transfer_em_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "tem_oracle" not in src, f

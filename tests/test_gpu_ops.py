@@ -1,0 +1,184 @@
+"""GPU parity, per op, through the C ABI: direct conv fwd / dgrad / wgrad vs the naive fp64 oracle on
+identical bf16-rounded operands; loss, Adam and uint8 kernels vs the oracle formulas."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import naive
+from oracle import tem_oracle as O
+from transfer_em_b200 import _lib
+from tests.gpu_helpers import (bf16r, conv_dgrad, conv_forward, conv_wgrad, make_desc, ptr, rel_l2, stream)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# tolerance of one bf16 output rounding (2^-9 relative) + accumulation-order noise
+BF16_RTOL, BF16_ATOL = 2.0 ** -8, 2e-3
+
+
+def _cuda(a, dt):
+    return torch.tensor(np.asarray(a), dtype=torch.float32).to(dt).to(DEV).contiguous()
+
+
+CASES = [
+    # k, s, cin, cout, transposed, dims(z,y,x), is3d
+    (3, 1, 8, 8, False, (9, 10, 11), True),
+    (3, 1, 16, 16, False, (7, 8, 13), True),
+    (3, 1, 32, 32, False, (6, 7, 9), True),
+    (3, 1, 8, 16, False, (8, 8, 8), True),
+    (3, 1, 16, 1, False, (8, 9, 10), True),      # g11: Cout = 1
+    (4, 2, 8, 8, False, (10, 12, 14), True),     # strided downsample
+    (4, 2, 32, 32, False, (6, 6, 8), True),
+    (4, 2, 32, 16, True, (5, 6, 7), True),       # convT k4 s2 SAME
+    (4, 2, 16, 8, True, (6, 5, 4), True),
+    (1, 1, 32, 32, False, (1, 1, 1), True),      # d7
+    (3, 1, 4, 2, False, (6, 6, 7), True),        # wf=32 widths (scalar-channel path)
+    (3, 1, 8, 8, False, (1, 12, 13), False),     # 2-D
+    (4, 2, 8, 8, False, (1, 12, 14), False),
+    (4, 2, 16, 8, True, (1, 7, 6), False),
+]
+
+
+@pytest.mark.parametrize("k,s,cin,cout,tr,dims,is3d", CASES)
+def test_conv_fwd_dgrad_wgrad(k, s, cin, cout, tr, dims, is3d):
+    r = np.random.default_rng(hash((k, s, cin, cout, tr, dims)) & 0xFFFF)
+    B = 2
+    kk = (k, k, k) if is3d else (1, k, k)
+    x = bf16r(r.standard_normal((B,) + dims + (cin,)))
+    wshape = kk + ((cout, cin) if tr else (cin, cout))
+    w = bf16r(r.standard_normal(wshape) * 0.2)
+    slope = 0.3
+    out_dt = torch.float32 if cout == 1 else torch.bfloat16
+    d = make_desc(B, dims, cin, cout, k, s, tr, slope, 0, torch.bfloat16, out_dt, is3d=is3d)
+    xg, wg = _cuda(x, torch.bfloat16), _cuda(w, torch.float32)
+    # ---- forward
+    y = conv_forward(xg, wg, d).float().cpu().numpy()
+    pre = naive.convT_fwd(x, w) if tr else naive.conv_fwd(x, w, s)
+    ref = naive.lrelu(pre, slope)
+    assert y.shape == ref.shape
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    assert rel_l2(y, ref) < 4e-3
+    # ---- data gradient, fused with LeakyReLU' of the producer's stored activation
+    dy = bf16r(r.standard_normal(ref.shape))
+    act = bf16r(r.standard_normal(x.shape))
+    dyg, actg = _cuda(dy, torch.bfloat16), _cuda(act, torch.bfloat16)
+    dx = conv_dgrad(dyg, wg, d, actg, 0.3).float().cpu().numpy()
+    dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
+    assert rel_l2(dx, dref) < 4e-3
+    # ---- weight gradient (fp32 accumulate, atomics)
+    dw = conv_wgrad(xg, dyg, d, wshape).cpu().numpy()
+    wref = naive.convT_wgrad(x, dy, kk) if tr else naive.conv_wgrad(x, dy, s, kk)
+    assert rel_l2(dw, wref) < 1e-5
+    np.testing.assert_allclose(dw, wref, rtol=1e-4, atol=1e-3)
+
+
+def test_first_layer_uint8_fused_standardize():
+    """k1: uint8 input standardised on load (datasets.py:157-163,193-202) -> conv3 -> LReLU."""
+    r = np.random.default_rng(3)
+    u = r.integers(0, 256, (2, 9, 10, 11, 1), dtype=np.uint8)
+    ms = (0.07, 0.61)
+    w = bf16r(r.standard_normal((3, 3, 3, 1, 8)) * 0.3)
+    d = make_desc(2, (9, 10, 11), 1, 8, 3, 1, False, 0.3, 0, torch.uint8, torch.bfloat16, ms)
+    y = conv_forward(torch.tensor(u).to(DEV), _cuda(w, torch.float32), d).float().cpu().numpy()
+    xs = O.standardize_population(O.scale_tensor(u[..., 0]), ms).astype(np.float64)
+    ref = naive.lrelu(naive.conv_fwd(xs, w, 1), 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    # wgrad w.r.t. the same uint8 input
+    dy = bf16r(r.standard_normal(ref.shape))
+    dw = conv_wgrad(torch.tensor(u).to(DEV), _cuda(dy, torch.bfloat16), d, (3, 3, 3, 1, 8)).cpu().numpy()
+    assert rel_l2(dw, naive.conv_wgrad(xs, dy, 1, (3, 3, 3))) < 1e-5
+
+
+def test_dropout_mask_and_forward():
+    key = 0xC0FFEE11
+    n = 2 * 6 * 8 * 10 * 8
+    m = torch.empty(n, dtype=torch.float32, device=DEV)
+    _lib.check(_lib.load().tem_dropout_mask(key, ptr(m), n, stream()))
+    torch.cuda.synchronize()
+    ref = O.dropout_keep_mask(key, (n,))
+    assert np.array_equal(m.cpu().numpy(), ref)          # bit-exact hash parity with the oracle
+    r = np.random.default_rng(5)
+    x = bf16r(r.standard_normal((2, 3, 4, 5, 16)))
+    w = bf16r(r.standard_normal((4, 4, 4, 8, 16)) * 0.2)
+    d = make_desc(2, (3, 4, 5), 16, 8, 4, 2, True, 0.3, key)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w, torch.float32), d).float().cpu().numpy()
+    pre = naive.convT_fwd(x, w)
+    mask = O.dropout_keep_mask(key, pre.shape)
+    ref = naive.lrelu(pre * mask * 2.0, 0.3)              # Dropout(0.5) then LeakyReLU (utils.py:134-135)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
+def test_bias_last_layer():
+    r = np.random.default_rng(6)
+    x = bf16r(r.standard_normal((3, 1, 1, 1, 32)))
+    w = bf16r(r.standard_normal((1, 1, 1, 32, 1)))
+    b = np.array([0.37], np.float32)
+    d = make_desc(3, (1, 1, 1), 32, 1, 1, 1, False, 1.0, 0, torch.bfloat16, torch.float32)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w, torch.float32), d, bias=torch.tensor(b).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(y, naive.conv_fwd(x, w, 1) + 0.37, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("target", [1.0, 0.0])
+def test_focal_logits_kernel(target):
+    r = np.random.default_rng(7)
+    x = (r.standard_normal(37) * 3).astype(np.float32)
+    xg = torch.tensor(x).to(DEV)
+    loss = torch.zeros(1, device=DEV); grad = torch.empty(37, device=DEV)
+    _lib.check(_lib.load().tem_focal_logits(ptr(xg), 37, target, 2.0, 2.0, ptr(loss), ptr(grad), stream()))
+    torch.cuda.synchronize()
+    l, g = naive.focal_logits_and_grad(x, int(target))
+    np.testing.assert_allclose(loss.item(), 2 * l.mean(), rtol=2e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), 2 * g / 37, rtol=2e-4, atol=1e-7)
+    xt = torch.tensor(x[:, None], dtype=torch.float64)
+    assert abs(loss.item() - 2 * float(O.focal_logits(target, xt))) < 1e-5
+
+
+def test_focal_probs_kernel():
+    r = np.random.default_rng(8)
+    a = (r.standard_normal(4099) * 1.2).astype(np.float32)
+    b = (r.standard_normal(4099) * 1.5).astype(np.float32)
+    a[:5] = b[:5]                       # exact ties: zero gradient
+    ag, bg = torch.tensor(a).to(DEV), torch.tensor(b).to(DEV)
+    loss = torch.zeros(1, device=DEV); grad = torch.empty(4099, device=DEV)
+    _lib.check(_lib.load().tem_focal_probs(ptr(ag), ptr(bg), 4099, 2.0, 4.0, ptr(loss), ptr(grad), stream()))
+    torch.cuda.synchronize()
+    l, g = naive.focal_nl_and_grad(a, b)
+    np.testing.assert_allclose(loss.item(), 4 * l.mean(), rtol=5e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), 4 * g / 4099, rtol=5e-4, atol=1e-8)
+    ref = float(O.calc_cycle_loss(torch.tensor(a, dtype=torch.float64)[:, None], torch.tensor(b, dtype=torch.float64)[:, None]))
+    assert abs(loss.item() - ref) / ref < 5e-5
+
+
+def test_keras_adam_kernel():
+    r = np.random.default_rng(9)
+    n = 10007
+    p = r.standard_normal(n).astype(np.float32); g = (r.standard_normal(n) * 1e-3).astype(np.float32)
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    pg, gg, mg, vg = (torch.tensor(t).to(DEV) for t in (p, g, m, v))
+    for t in (1, 2, 3):
+        _lib.check(_lib.load().tem_adam(ptr(pg), ptr(gg), ptr(mg), ptr(vg), n, t, 2e-4, 0.5, 0.999, 1e-7, 1.0, stream()))
+        p, m, v = O.keras_adam_update(p.astype(np.float64), g.astype(np.float64), m.astype(np.float64), v.astype(np.float64), t)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(pg.cpu().numpy(), p, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mg.cpu().numpy(), m, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(vg.cpu().numpy(), v, rtol=1e-5, atol=1e-12)
+
+
+def test_uint8_conventions_bit_exact():
+    """scale/standardise and (y*std+mean+1)*127.5 -> rint -> wrap must be bit-exact (utils.py:109,118)."""
+    from transfer_em_b200 import datasets as D
+    r = np.random.default_rng(10)
+    u = r.integers(0, 256, (3, 17, 19), dtype=np.uint8)
+    for ms in [(0.0, 1.0), (0.0, 0.5774), (-0.113, 0.731)]:
+        t = D.scale_and_standardize(u, ms)
+        ref = O.standardize_population(O.scale_tensor(u), ms)
+        assert t.dtype == np.float32 and np.array_equal(t, ref)
+        y = (r.standard_normal(200003) * 1.3).astype(np.float32)
+        y[:9] = np.array([(0.5 / 127.5 - 1 - ms[0]) / ms[1], (1.5 / 127.5 - 1 - ms[0]) / ms[1], 5.0, -5.0, 0.0, 1e-3, -1e-3, 2.0, -2.0], np.float32)
+        q = D.unstandardize_to_uint8(y, ms)
+        assert q.dtype == np.uint8 and np.array_equal(q, O.to_uint8_reference(y, ms))
+        back = D.unstandardize_to_uint8(ref, ms)
+        assert np.array_equal(back[..., 0], u)           # round trip uint8 -> float -> uint8 is the identity

@@ -1,0 +1,141 @@
+// Shared device/host definitions for the transfer_em_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+enum { DT_U8 = 0, DT_BF16 = 1, DT_F32 = 2 };
+
+// A view of a dense channels-last tensor [B,Z,Y,X,C] (C = channel pitch).  `shift` maps the logical
+// coordinate system of an op to tensor coordinates (negative = virtual zero padding, positive = crop
+// window).  `origins` (optional) gives a per-sample (z,y,x) origin into one shared volume
+// (tiled inference: transfer_em/utils.py:77-89 without the gather copy).
+struct SrcView {
+  const void* p;
+  const int* origins;
+  long long bstride;   // elements between samples (ignored when origins != nullptr)
+  int dtype;
+  int Z, Y, X;
+  int C, coff;
+  int shift[3];
+};
+
+struct ConvArgs {
+  SrcView s0, s1;      // s1: second source of a fused crop-and-concat (generator.py:74-86)
+  int C0, C1;          // input channels taken from s0 / s1
+  const float* w;      // fp32 master weights
+  long long ws_tap, ws_in, ws_out;   // element strides: tap, op-input channel, op-output channel
+  const float* bias;
+  int k[3], stride[3], pad[3];
+  int form;            // 0: out[o] = sum_k in[s*o + k - pad] w[k]   (conv fwd, convT dgrad)
+                       // 1: out[j] = sum_{k: (j+pad-k)%s==0} in[(j+pad-k)/s] w[k]  (conv dgrad, convT fwd)
+  int B;
+  int L[3];            // logical output extent computed by this launch
+  int conv_off[3];     // conv coordinate = logical + conv_off
+  void* out; int out_dtype;
+  int OZ, OY, OX, out_C, out_coff, out_off[3];
+  int Cout;
+  float slope;         // forward LeakyReLU slope (1 = linear)
+  const bf16* ref;     // backward: multiply by (ref > 0 ? 1 : ref_slope)
+  int RZ, RY, RX, ref_C, ref_coff, ref_off[3];
+  float ref_slope;
+  uint32_t drop_key;   // != 0: multiply by 2*keep(hash(idx ^ key)), idx = dense [B,L,Cout] index
+  int accumulate;      // out += result
+  int use_lut; float lut_mean, lut_std;   // u8 input: (u/127.5 - 1 - mean)/std
+  int ci_chunk;
+  long long nvox;      // voxels per parity class
+  int H[3];            // per-class extents (ceil(L/stride) for form 1, L for form 0)
+};
+
+struct WgradArgs {
+  SrcView S;           // tensor read at s*p + k - pad
+  int Ca;
+  const void* P; int p_dtype;
+  int PZ, PY, PX, p_C, p_coff, p_off[3];
+  long long p_bstride;
+  int Cb;
+  int B, L[3];
+  int k[3], stride[3], pad[3];
+  float* dw; long long ws_tap, ws_a, ws_b;
+  int use_lut; float lut_mean, lut_std;
+  long long nvox;
+  long long vox_per_cta;
+  int ncombo;
+};
+
+__host__ __device__ __forceinline__ uint32_t tem_hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ float tem_keep(uint32_t key, uint32_t idx) {
+  return (tem_hash32(idx ^ key) >> 31) ? 1.0f : 0.0f;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float tem_standardize(float u, float mean, float stdv) {
+  // scale_tensor + standardize_population, op order preserved (datasets.py:157-163,193-202)
+  float t = __fdiv_rn(u, 127.5f);
+  t = __fsub_rn(t, 1.0f);
+  t = __fsub_rn(t, mean);
+  return __fdiv_rn(t, stdv);
+}
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+#endif
+
+// launchers (conv_direct.cu)
+cudaError_t launch_conv_direct(const ConvArgs& a, cudaStream_t st);
+cudaError_t launch_wgrad_direct(const WgradArgs& a, cudaStream_t st);
+cudaError_t launch_bias_grad(const void* P, int p_dtype, long long nvox, int C, float* db, cudaStream_t st);
+
+// elementwise.cu
+cudaError_t launch_focal_logits(const float* x, long long n, float target, float gamma, float scale, int mode,
+                                float* loss_out, float* grad, cudaStream_t st);
+struct PairLossArgs {
+  SrcView a;           // reference image window (u8 w/ LUT, or f32); shift = crop
+  const float* b;      // generated fp32 dense [B, n, n, n, 1]
+  int B, N[3];         // dims of b
+  int crop[3];         // loss window = b[crop : N-crop]
+  float gamma, scale;  // grad = scale * dl/db / count ; loss_out += scale * mean(l)
+  int mode;            // 0 focal-probs (cgan.py:122-142), 1 L1
+  int use_lut; float lut_mean, lut_std;
+  float* loss_out; float* grad;   // grad dense like b (zeros outside the window)
+};
+cudaError_t launch_pair_loss(const PairLossArgs& a, cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
+                        float eps, float gscale, cudaStream_t st);
+cudaError_t launch_standardize_u8(const uint8_t* in, float* out, long long n, float mean, float stdv, cudaStream_t st);
+cudaError_t launch_unstandardize_u8(const float* in, uint8_t* out, long long n, float mean, float stdv, cudaStream_t st);
+cudaError_t launch_dropout_mask(uint32_t key, float* out, long long n, cudaStream_t st);
+cudaError_t launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t st);
+cudaError_t launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
+cudaError_t launch_init_normal(float* p, long long n, uint64_t seed, float stdv, cudaStream_t st);
+struct StitchArgs {
+  const float* y;      // generator output fp32 [T, od+2*tpad, .., 1]
+  const int* index;    // [T][3] (x,y,z) output index of each tile (utils.py:84)
+  int T, ydim, tpad, od;
+  float mean, stdv;
+  uint8_t* out; long long OZ, OY, OX;   // out[z,y,x], writes clipped to the request (utils.py:128-130)
+};
+cudaError_t launch_stitch_u8(const StitchArgs& a, cudaStream_t st);
+struct FetchInArgs {
+  const uint8_t* vol; long long VZ, VY, VX;
+  const int* origins;  // [T][3] (z,y,x) tile origin in the volume
+  const int* index;    // [T][3] (x,y,z)
+  int T, buf, od; float mean, stdv;
+  uint8_t* out; long long OZ, OY, OX;
+};
+cudaError_t launch_fetch_input_u8(const FetchInArgs& a, cudaStream_t st);

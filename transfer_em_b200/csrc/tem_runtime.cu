@@ -1,0 +1,1000 @@
+// libtem_b200 runtime: network tables, pass executors (forward / backward), train step, tiled
+// inference and the extern "C" ABI of include/transfer_em_b200.h.
+//
+// Reference interfaces replaced (paths relative to the reference repository):
+//   transfer_em/models/generator.py:22-117, discriminator.py:14-105, utils.py:41-137  (graphs)
+//   transfer_em/cgan.py:40-103 (construction), :110-142 (losses), :144-230 (train_step), :289-293 (predict)
+//   transfer_em/utils.py:41-130 (predict_ng_cube)
+#include "tem_runtime.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void tem_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* tem_last_error(void) { return g_err; }
+extern "C" int tem_abi_version(void) { return TEM_ABI_VERSION; }
+
+#define ARG_FAIL(...) do { tem_set_error(__VA_ARGS__); return TEM_ERR_ARG; } while (0)
+
+// ------------------------------------------------------------------------------------------
+// network tables
+// ------------------------------------------------------------------------------------------
+static LayerSpec mk(const char* name, int tr, int k, int s, int ci, int co, float slope, int drop = 0, int bias = 0) {
+  LayerSpec L; memset(&L, 0, sizeof(L));
+  snprintf(L.name, sizeof(L.name), "%s", name);
+  L.transposed = tr; L.k = k; L.stride = s; L.cin = ci; L.cout = co; L.slope = slope; L.dropout = drop; L.bias = bias;
+  return L;
+}
+
+static void finalize_net(NetSpec& N, int nd) {
+  long long off = 0;
+  for (auto& L : N.L) {
+    long long taps = 1; for (int i = 0; i < nd; ++i) taps *= L.k;
+    L.w_count = taps * L.cin * L.cout;
+    L.w_off = off; off += L.w_count;
+    if (L.bias) { L.b_off = off; off += L.cout; }
+  }
+  N.count = off;
+}
+
+// generator.py:54-110 (g0..g11)
+static NetSpec build_generator(int wf, int nd) {
+  const int c1 = 64 / wf, c2 = 128 / wf, c4 = 256 / wf;
+  const float a = 0.3f;   // LeakyReLU() default alpha [upstream]
+  NetSpec N; N.is_gen = 1;
+  N.L = { mk("g0", 0, 3, 1, 1, c1, a), mk("g1", 0, 3, 1, c1, c1, a), mk("g2", 0, 4, 2, c1, c1, a),
+          mk("g3", 0, 3, 1, c1, c2, a), mk("g4", 0, 4, 2, c2, c2, a), mk("g5", 0, 3, 1, c2, 2 * c2, a),
+          mk("g6", 1, 4, 2, 2 * c2, c2, a, 1), mk("g7", 0, 3, 1, 2 * c2, c4, a), mk("g8", 0, 3, 1, c4, 2 * c1, a),
+          mk("g9", 1, 4, 2, 2 * c1, c1, a, 1), mk("g10", 0, 3, 1, 2 * c1, c2, a), mk("g11", 0, 3, 1, c2, 1, 1.0f) };
+  finalize_net(N, nd);
+  return N;
+}
+
+// discriminator.py:39-99 (d0..d8); 16 -> 128//wf and dims=32 -> 256//wf generalised (identical at wf=8)
+static NetSpec build_discriminator(int wf, int nd) {
+  const int c1 = 64 / wf, c2 = 128 / wf, c4 = 256 / wf;
+  const float a = 0.3f;
+  NetSpec N; N.is_gen = 0;
+  N.L = { mk("d0", 0, 3, 1, 1, c1, a), mk("d1", 0, 4, 2, c1, c1, a),
+          mk("d2", 0, 3, 1, nd == 3 ? c1 : 1, c2, a),       // 2-D: HACK conv on the raw input (discriminator.py:49-51)
+          mk("d3", 0, 3, 1, c2, c4, a), mk("d4", 0, 4, 2, c4, c4, a), mk("d5", 0, 3, 1, c4, 32, a),
+          mk("d6", 0, 4, 2, 32, 32, a * a),                 // LeakyReLU applied twice (discriminator.py:73-74)
+          mk("d7", 0, 1, 1, 32, c4, a), mk("d8", 0, 1, 1, c4, 1, 1.0f, 0, 1) };
+  finalize_net(N, nd);
+  return N;
+}
+
+static void gen_dims(int n, int d[12]) {
+  d[0] = n - 2; d[1] = d[0] - 2; d[2] = (d[1] - 4) / 2 + 1; d[3] = d[2] - 2; d[4] = (d[3] - 4) / 2 + 1;
+  d[5] = d[4] - 2; d[6] = d[5] * 2; d[7] = d[6] - 2; d[8] = d[7] - 2; d[9] = d[8] * 2; d[10] = d[9] - 2; d[11] = d[10] - 2;
+}
+static int disc_first(int nd) { return nd == 3 ? 0 : 2; }
+static void disc_dims(int m, int nd, int d[9]) {
+  int cur = m;
+  for (int i = 0; i < 9; ++i) d[i] = 0;
+  static const int K[9] = {3, 4, 3, 3, 4, 3, 4, 1, 1}, S[9] = {1, 2, 1, 1, 2, 1, 2, 1, 1};
+  for (int i = disc_first(nd); i < 9; ++i) { cur = (cur - K[i]) / S[i] + 1; d[i] = cur; }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+static int dev_alloc(tem_handle* h, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { tem_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return TEM_ERR_CUDA; }
+  h->allocs.push_back(*p);
+  return TEM_OK;
+}
+
+static void set3(int* dst, int a, int b, int c) { dst[0] = a; dst[1] = b; dst[2] = c; }
+static void spatial(const tem_handle* h, int edge, int d[3]) { set3(d, h->nd == 3 ? edge : 1, edge, edge); }
+static void axes(const tem_handle* h, int v, int neutral, int d[3]) { set3(d, h->nd == 3 ? v : neutral, v, v); }
+
+static int alloc_tensor(tem_handle* h, Tensor& t, int dtype, int B, int edge, int C) {
+  t.dtype = dtype; t.C = C; spatial(h, edge, t.d);
+  const size_t es = dtype == DT_F32 ? 4 : (dtype == DT_BF16 ? 2 : 1);
+  return dev_alloc(h, &t.p, (size_t)B * t.per_sample() * es);
+}
+
+static SrcView view_of(const Tensor& t, int coff = 0) {
+  SrcView v; memset(&v, 0, sizeof(v));
+  v.p = t.p; v.dtype = t.dtype; v.Z = t.d[0]; v.Y = t.d[1]; v.X = t.d[2]; v.C = t.C; v.coff = coff;
+  v.bstride = t.per_sample();
+  return v;
+}
+static SrcView view_of_input(const InputRef& in) {
+  SrcView v; memset(&v, 0, sizeof(v));
+  v.p = in.p; v.dtype = in.dtype; v.Z = in.dims[0]; v.Y = in.dims[1]; v.X = in.dims[2]; v.C = 1; v.coff = 0;
+  v.bstride = (long long)in.dims[0] * in.dims[1] * in.dims[2];
+  v.origins = in.origins;
+  for (int i = 0; i < 3; ++i) v.shift[i] = in.shift[i];
+  return v;
+}
+
+static void layer_axes(const tem_handle* h, const LayerSpec& L, int k[3], int s[3], int pad[3]) {
+  axes(h, L.k, 1, k); axes(h, L.stride, 1, s);
+  if (L.transposed) axes(h, 1, 0, pad); else set3(pad, 0, 0, 0);
+}
+
+static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) {
+  a.out = out.p; a.out_dtype = out.dtype; a.OZ = out.d[0]; a.OY = out.d[1]; a.OX = out.d[2]; a.out_C = out.C; a.out_coff = coff;
+  for (int i = 0; i < 3; ++i) a.out_off[i] = off ? off[i] : 0;
+}
+
+// forward of one layer: out = act(dropout(conv(cat(s0,s1)) + bias))
+static int run_forward(const tem_handle* h, const LayerSpec& L, const float* netp, const SrcView& s0, int C0,
+                       const SrcView* s1, int C1, const Tensor& out, int B, uint32_t drop_key,
+                       int use_lut, float mean, float stdv, cudaStream_t st) {
+  ConvArgs a; memset(&a, 0, sizeof(a));
+  a.s0 = s0; a.C0 = C0; a.C1 = C1; if (s1) a.s1 = *s1;
+  a.w = netp + L.w_off; a.bias = L.bias ? netp + L.b_off : nullptr;
+  layer_axes(h, L, a.k, a.stride, a.pad);
+  if (!L.transposed) { a.form = 0; a.ws_tap = (long long)L.cin * L.cout; a.ws_in = L.cout; a.ws_out = 1; }
+  else { a.form = 1; a.ws_tap = (long long)L.cin * L.cout; a.ws_in = 1; a.ws_out = L.cin; }   // Keras [k][co][ci]
+  a.B = B; for (int i = 0; i < 3; ++i) a.L[i] = out.d[i];
+  set_out(a, out, 0, nullptr);
+  a.Cout = L.cout; a.slope = L.slope; a.drop_key = L.dropout ? drop_key : 0;
+  a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
+  TEM_CUDA(launch_conv_direct(a, st));
+  return TEM_OK;
+}
+
+// data gradient of layer L restricted to op-output channels [ci_off, ci_off+ci_cnt) of its input:
+//   out(window) (+)= dgrad(dy, w) * lrelu'(ref) * dropout
+static int run_dgrad(const tem_handle* h, const LayerSpec& L, const float* netp, const Tensor& dy, int ci_off, int ci_cnt,
+                     const Tensor& out, int out_coff, const int out_off[3], const int ext[3], const int conv_off[3],
+                     const Tensor* ref, const int ref_off[3], float ref_slope, uint32_t drop_key, int accumulate,
+                     int B, cudaStream_t st) {
+  ConvArgs a; memset(&a, 0, sizeof(a));
+  a.s0 = view_of(dy); a.C0 = L.cout; a.C1 = 0;
+  layer_axes(h, L, a.k, a.stride, a.pad);
+  if (!L.transposed) {   // conv dgrad: form 1; op-in = cout (stride 1), op-out = cin (stride cout)
+    a.form = 1; a.ws_tap = (long long)L.cin * L.cout; a.ws_in = 1; a.ws_out = L.cout;
+    a.w = netp + L.w_off + (long long)ci_off * L.cout;
+  } else {               // convT dgrad: strided conv, pad 1; Keras [k][co][ci]
+    a.form = 0; a.ws_tap = (long long)L.cin * L.cout; a.ws_in = L.cin; a.ws_out = 1;
+    a.w = netp + L.w_off + ci_off;
+  }
+  a.B = B;
+  for (int i = 0; i < 3; ++i) { a.L[i] = ext[i]; a.conv_off[i] = conv_off ? conv_off[i] : 0; }
+  set_out(a, out, out_coff, out_off);
+  a.Cout = ci_cnt; a.slope = 1.0f;
+  if (ref) {
+    a.ref = (const bf16*)ref->p; a.RZ = ref->d[0]; a.RY = ref->d[1]; a.RX = ref->d[2]; a.ref_C = ref->C; a.ref_coff = 0;
+    for (int i = 0; i < 3; ++i) a.ref_off[i] = ref_off ? ref_off[i] : 0;
+    a.ref_slope = ref_slope;
+  }
+  a.drop_key = drop_key; a.accumulate = accumulate;
+  TEM_CUDA(launch_conv_direct(a, st));
+  return TEM_OK;
+}
+
+// weight gradient of layer L w.r.t. input channels [ci_off, ci_off+ci_cnt) taken from `x`
+static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const SrcView& x, int ci_off, int ci_cnt,
+                     const Tensor& dy, int B, int use_lut, float mean, float stdv, cudaStream_t st) {
+  WgradArgs a; memset(&a, 0, sizeof(a));
+  layer_axes(h, L, a.k, a.stride, a.pad);
+  a.B = B;
+  if (!L.transposed) {
+    a.S = x; a.Ca = ci_cnt;
+    a.P = dy.p; a.p_dtype = dy.dtype; a.PZ = dy.d[0]; a.PY = dy.d[1]; a.PX = dy.d[2]; a.p_C = dy.C; a.p_coff = 0;
+    a.p_bstride = dy.per_sample(); a.Cb = L.cout;
+    for (int i = 0; i < 3; ++i) a.L[i] = dy.d[i];
+    a.dw = netg + L.w_off + (long long)ci_off * L.cout;
+    a.ws_tap = (long long)L.cin * L.cout; a.ws_a = L.cout; a.ws_b = 1;
+  } else {
+    // dw[k][co][ci] = sum_i x[i][ci] dy[2i+k-1][co]: strided tensor = dy, position tensor = x
+    a.S = view_of(dy); a.Ca = L.cout;
+    a.P = x.p; a.p_dtype = x.dtype; a.PZ = x.Z; a.PY = x.Y; a.PX = x.X; a.p_C = x.C; a.p_coff = x.coff;
+    a.p_bstride = x.bstride; a.Cb = L.cin;
+    set3(a.L, x.Z, x.Y, x.X);
+    a.dw = netg + L.w_off;
+    a.ws_tap = (long long)L.cin * L.cout; a.ws_a = L.cin; a.ws_b = 1;
+  }
+  a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
+  TEM_CUDA(launch_wgrad_direct(a, st));
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generator passes
+// ------------------------------------------------------------------------------------------
+static int gen_forward(tem_handle* h, int net, GenPass& P, const InputRef& in, int B, int n, const uint32_t keys[2], cudaStream_t st) {
+  const NetSpec& N = h->nets[net];
+  const float* w = h->params + N.arena_off;
+  int d[12]; gen_dims(n, d);
+  for (int i = 0; i < 12; ++i) spatial(h, d[i], P.a[i].d);
+  P.in = in; P.B = B; P.n = n; P.keys[0] = keys ? keys[0] : 0; P.keys[1] = keys ? keys[1] : 0; P.valid = true;
+  const int crop1 = (d[3] - d[6]) / 2, crop0 = (d[1] - d[9]) / 2;   // generator.py:75 (low side)
+  SrcView vin = view_of_input(in);
+  TEM_CHECK(run_forward(h, N.L[0], w, vin, 1, nullptr, 0, P.a[0], B, 0, in.use_lut, in.mean, in.stdv, st));
+  for (int i = 1; i <= 5; ++i)
+    TEM_CHECK(run_forward(h, N.L[i], w, view_of(P.a[i - 1]), N.L[i].cin, nullptr, 0, P.a[i], B, 0, 0, 0, 0, st));
+  TEM_CHECK(run_forward(h, N.L[6], w, view_of(P.a[5]), N.L[6].cin, nullptr, 0, P.a[6], B, P.keys[0], 0, 0, 0, st));
+  {
+    SrcView s1 = view_of(P.a[3]); axes(h, crop1, 0, s1.shift);
+    TEM_CHECK(run_forward(h, N.L[7], w, view_of(P.a[6]), N.L[6].cout, &s1, N.L[3].cout, P.a[7], B, 0, 0, 0, 0, st));
+  }
+  TEM_CHECK(run_forward(h, N.L[8], w, view_of(P.a[7]), N.L[8].cin, nullptr, 0, P.a[8], B, 0, 0, 0, 0, st));
+  TEM_CHECK(run_forward(h, N.L[9], w, view_of(P.a[8]), N.L[9].cin, nullptr, 0, P.a[9], B, P.keys[1], 0, 0, 0, st));
+  {
+    SrcView s1 = view_of(P.a[1]); axes(h, crop0, 0, s1.shift);
+    TEM_CHECK(run_forward(h, N.L[10], w, view_of(P.a[9]), N.L[9].cout, &s1, N.L[1].cout, P.a[10], B, 0, 0, 0, 0, st));
+  }
+  TEM_CHECK(run_forward(h, N.L[11], w, view_of(P.a[10]), N.L[11].cin, nullptr, 0, P.a[11], B, 0, 0, 0, 0, st));
+  return TEM_OK;
+}
+
+// backward of one generator pass.  dout: fp32 gradient w.r.t. the pass output.  If d_in != nullptr the
+// gradient w.r.t. the (zero-padded) input is accumulated into it over the un-padded window (cgan.py:161,170).
+static int gen_backward(tem_handle* h, int net, GenPass& P, float* dout, float* d_in, cudaStream_t st) {
+  const NetSpec& N = h->nets[net];
+  const float* w = h->params + N.arena_off;
+  float* g = h->grads + N.arena_off;
+  const int B = P.B;
+  int d[12]; gen_dims(P.n, d);
+  Tensor dP[12];
+  for (int i = 0; i < 11; ++i) { dP[i] = h->gdP[i]; spatial(h, d[i], dP[i].d); }
+  dP[11] = P.a[11]; dP[11].p = dout;
+  const int crop1 = (d[3] - d[6]) / 2, crop0 = (d[1] - d[9]) / 2;
+  int c1v[3], c0v[3]; axes(h, crop1, 0, c1v); axes(h, crop0, 0, c0v);
+  // skip gradients receive a window write first, then a full accumulate
+  TEM_CUDA(cudaMemsetAsync(dP[1].p, 0, (size_t)B * dP[1].per_sample() * 2, st));
+  TEM_CUDA(cudaMemsetAsync(dP[3].p, 0, (size_t)B * dP[3].per_sample() * 2, st));
+
+  auto plain = [&](int li) -> int {   // layer li with single-source input a[li-1]
+    const LayerSpec& L = N.L[li];
+    const LayerSpec& Lp = N.L[li - 1];
+    if (!L.transposed) TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[li - 1]), 0, L.cin, dP[li], B, 0, 0, 0, st));
+    else TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[li - 1]), 0, L.cin, dP[li], B, 0, 0, 0, st));
+    const uint32_t key = Lp.dropout ? (li - 1 == 6 ? P.keys[0] : P.keys[1]) : 0;
+    const bool acc = (li - 1 == 1 || li - 1 == 3);      // skip tensors accumulate the down-path gradient
+    TEM_CHECK(run_dgrad(h, L, w, dP[li], 0, L.cin, dP[li - 1], 0, nullptr, dP[li - 1].d, nullptr,
+                        &P.a[li - 1], nullptr, Lp.slope, key, acc ? 1 : 0, B, st));
+    return TEM_OK;
+  };
+  auto cat = [&](int li, int up, int skip, const int cropv[3]) -> int {   // layer li with input cat(a[up], crop(a[skip]))
+    const LayerSpec& L = N.L[li];
+    const int cu = N.L[up].cout, cs = N.L[skip].cout;
+    TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[up]), 0, cu, dP[li], B, 0, 0, 0, st));
+    SrcView sv = view_of(P.a[skip]); for (int i = 0; i < 3; ++i) sv.shift[i] = cropv[i];
+    TEM_CHECK(run_wgrad(h, L, g, sv, cu, cs, dP[li], B, 0, 0, 0, st));
+    const uint32_t key = N.L[up].dropout ? (up == 6 ? P.keys[0] : P.keys[1]) : 0;
+    TEM_CHECK(run_dgrad(h, L, w, dP[li], 0, cu, dP[up], 0, nullptr, dP[up].d, nullptr, &P.a[up], nullptr, N.L[up].slope, key, 0, B, st));
+    TEM_CHECK(run_dgrad(h, L, w, dP[li], cu, cs, dP[skip], 0, cropv, dP[up].d, nullptr, &P.a[skip], cropv, N.L[skip].slope, 0, 0, B, st));
+    return TEM_OK;
+  };
+  TEM_CHECK(plain(11));
+  TEM_CHECK(cat(10, 9, 1, c0v));
+  TEM_CHECK(plain(9)); TEM_CHECK(plain(8));
+  TEM_CHECK(cat(7, 6, 3, c1v));
+  for (int li = 6; li >= 1; --li) TEM_CHECK(plain(li));
+  // g0: weight gradient w.r.t. the pass input, optional input gradient over the un-padded window
+  SrcView vin = view_of_input(P.in);
+  TEM_CHECK(run_wgrad(h, N.L[0], g, vin, 0, 1, dP[0], B, P.in.use_lut, P.in.mean, P.in.stdv, st));
+  if (d_in) {
+    Tensor din; din.p = d_in; din.dtype = DT_F32; din.C = 1; set3(din.d, P.in.dims[0], P.in.dims[1], P.in.dims[2]);
+    int coff[3]; for (int i = 0; i < 3; ++i) coff[i] = -P.in.shift[i];    // window of the padded input
+    TEM_CHECK(run_dgrad(h, N.L[0], w, dP[0], 0, 1, din, 0, nullptr, din.d, coff, nullptr, nullptr, 1.f, 0, 1, B, st));
+  }
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// discriminator passes
+// ------------------------------------------------------------------------------------------
+static int disc_forward(tem_handle* h, int net, DiscPass& P, const InputRef& in, int B, int m, cudaStream_t st) {
+  const NetSpec& N = h->nets[net];
+  const float* w = h->params + N.arena_off;
+  int d[9]; disc_dims(m, h->nd, d);
+  if (d[8] < 1) ARG_FAIL("discriminator input edge %d too small", m);
+  for (int i = 0; i < 9; ++i) spatial(h, d[i] > 0 ? d[i] : 1, P.a[i].d);
+  P.in = in; P.B = B; P.m = m; P.valid = true;
+  const int f = disc_first(h->nd);
+  SrcView vin = view_of_input(in);
+  TEM_CHECK(run_forward(h, N.L[f], w, vin, 1, nullptr, 0, P.a[f], B, 0, in.use_lut, in.mean, in.stdv, st));
+  for (int i = f + 1; i < 9; ++i)
+    TEM_CHECK(run_forward(h, N.L[i], w, view_of(P.a[i - 1]), N.L[i].cin, nullptr, 0, P.a[i], B, 0, 0, 0, 0, st));
+  return TEM_OK;
+}
+
+static int disc_backward(tem_handle* h, int net, DiscPass& P, float* dlogits, bool do_wgrad, float* d_in, cudaStream_t st) {
+  const NetSpec& N = h->nets[net];
+  const float* w = h->params + N.arena_off;
+  float* g = h->grads + N.arena_off;
+  const int B = P.B;
+  int d[9]; disc_dims(P.m, h->nd, d);
+  Tensor dP[9];
+  for (int i = 0; i < 8; ++i) { dP[i] = h->ddP[i]; spatial(h, d[i] > 0 ? d[i] : 1, dP[i].d); }
+  dP[8] = P.a[8]; dP[8].p = dlogits;
+  const int f = disc_first(h->nd);
+  for (int li = 8; li > f; --li) {
+    const LayerSpec& L = N.L[li];
+    if (do_wgrad) {
+      TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[li - 1]), 0, L.cin, dP[li], B, 0, 0, 0, st));
+      if (L.bias) TEM_CUDA(launch_bias_grad(dP[li].p, dP[li].dtype, (long long)B * dP[li].d[0] * dP[li].d[1] * dP[li].d[2], L.cout, g + L.b_off, st));
+    }
+    TEM_CHECK(run_dgrad(h, L, w, dP[li], 0, L.cin, dP[li - 1], 0, nullptr, dP[li - 1].d, nullptr, &P.a[li - 1], nullptr,
+                        N.L[li - 1].slope, 0, 0, B, st));
+  }
+  SrcView vin = view_of_input(P.in);
+  if (do_wgrad) TEM_CHECK(run_wgrad(h, N.L[f], g, vin, 0, 1, dP[f], B, P.in.use_lut, P.in.mean, P.in.stdv, st));
+  if (d_in) {
+    Tensor din; din.p = d_in; din.dtype = DT_F32; din.C = 1; set3(din.d, P.in.dims[0], P.in.dims[1], P.in.dims[2]);
+    TEM_CHECK(run_dgrad(h, N.L[f], w, dP[f], 0, 1, din, 0, nullptr, din.d, nullptr, nullptr, nullptr, 1.f, 0, 0, B, st));
+  }
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL (loaded at run time: libnccl.so.2 is already resident in a torch process)
+// ------------------------------------------------------------------------------------------
+typedef struct { char b[128]; } tem_nccl_id;
+struct NcclApi {
+  void* lib;
+  int (*GetUniqueId)(void*);
+  int (*CommInitRank)(void**, int, tem_nccl_id, int);
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*CommDestroy)(void*);
+  const char* (*GetErrorString)(int);
+};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static int load_nccl() {
+  if (g_nccl.lib) return TEM_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) { tem_set_error("cannot load libnccl.so.2: %s", dlerror()); return TEM_ERR_NCCL; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+  *(void**)(&g_nccl.CommInitRank) = dlsym(lib, "ncclCommInitRank");
+  *(void**)(&g_nccl.AllReduce) = dlsym(lib, "ncclAllReduce");
+  *(void**)(&g_nccl.Broadcast) = dlsym(lib, "ncclBroadcast");
+  *(void**)(&g_nccl.CommDestroy) = dlsym(lib, "ncclCommDestroy");
+  *(void**)(&g_nccl.GetErrorString) = dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
+    tem_set_error("libnccl is missing required symbols"); return TEM_ERR_NCCL;
+  }
+  g_nccl.lib = lib;
+  return TEM_OK;
+}
+#define TEM_NCCL(expr)                                                                           \
+  do {                                                                                           \
+    int _r = (expr);                                                                             \
+    if (_r != 0) {                                                                               \
+      tem_set_error("%s:%d NCCL error %d: %s", __FILE__, __LINE__, _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+      return TEM_ERR_NCCL;                                                                       \
+    }                                                                                            \
+  } while (0)
+enum { kNcclFloat32 = 7, kNcclSum = 0 };
+
+extern "C" int tem_comm_unique_id(uint8_t id[128]) {
+  TEM_CHECK(load_nccl());
+  TEM_NCCL(g_nccl.GetUniqueId(id));
+  return TEM_OK;
+}
+extern "C" int tem_comm_init(tem_handle* h, const uint8_t id[128], int rank, int world) {
+  if (!h || !id || world < 1 || rank < 0 || rank >= world) ARG_FAIL("tem_comm_init: bad arguments");
+  TEM_CHECK(load_nccl());
+  TEM_CUDA(cudaSetDevice(h->cfg.device));
+  tem_nccl_id uid; memcpy(uid.b, id, 128);
+  TEM_NCCL(g_nccl.CommInitRank(&h->comm, world, uid, rank));
+  h->rank = rank; h->world = world;
+  return TEM_OK;
+}
+extern "C" int tem_comm_world(const tem_handle* h, int* rank, int* world) {
+  if (!h) ARG_FAIL("null handle");
+  if (rank) *rank = h->rank; if (world) *world = h->world;
+  return TEM_OK;
+}
+extern "C" int tem_comm_sync_params(tem_handle* h, void* stream) {
+  if (!h) ARG_FAIL("null handle");
+  if (!h->comm) return TEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  TEM_NCCL(g_nccl.Broadcast(h->params, h->params, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
+  TEM_NCCL(g_nccl.Broadcast(h->adam_m, h->adam_m, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
+  TEM_NCCL(g_nccl.Broadcast(h->adam_v, h->adam_v, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------
+extern "C" void tem_default_config(tem_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = TEM_ABI_VERSION; c->device = 0; c->is3d = 1; c->wf = 8; c->dimsize = 74; c->max_batch = 1;
+  c->loss_mode = TEM_LOSS_FOCAL; c->dropout = 1; c->focal_gamma = 2.0f;
+  c->lr = 2e-4f; c->beta1 = 0.5f; c->beta2 = 0.999f; c->eps = 1e-7f; c->seed = 0; c->train = 1; c->use_tensor_cores = 1;
+}
+
+static int alloc_gen_pass(tem_handle* h, GenPass& P, int B, int n) {
+  int d[12]; gen_dims(n, d);
+  const NetSpec& N = h->nets[TEM_NET_G];
+  for (int i = 0; i < 11; ++i) TEM_CHECK(alloc_tensor(h, P.a[i], DT_BF16, B, d[i], N.L[i].cout));
+  TEM_CHECK(alloc_tensor(h, P.a[11], DT_F32, B, d[11], 1));
+  P.valid = false;
+  return TEM_OK;
+}
+static int alloc_disc_pass(tem_handle* h, DiscPass& P, int B, int m) {
+  int d[9]; disc_dims(m, h->nd, d);
+  const NetSpec& N = h->nets[TEM_NET_DX];
+  for (int i = 0; i < 8; ++i) TEM_CHECK(alloc_tensor(h, P.a[i], DT_BF16, B, d[i] > 0 ? d[i] : 1, N.L[i].cout));
+  TEM_CHECK(alloc_tensor(h, P.a[8], DT_F32, B, d[8], 1));
+  P.valid = false;
+  return TEM_OK;
+}
+
+extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
+  if (!cfg || !out) ARG_FAIL("tem_create: null argument");
+  if (cfg->abi_version != TEM_ABI_VERSION) ARG_FAIL("ABI version mismatch: header %d, library %d", cfg->abi_version, TEM_ABI_VERSION);
+  if (cfg->dimsize < 74) ARG_FAIL("minimum dimension allowed is 74");                       // cgan.py:52-53
+  if (cfg->dimsize % 4 != 2) ARG_FAIL("%d does not allow for valid convolutions", cfg->dimsize);   // generator.py:37-38 (superset: n = 2 mod 4)
+  const int wf = cfg->wf;
+  if (!(wf == 1 || wf == 2 || wf == 4 || wf == 8 || wf == 16 || wf == 32)) ARG_FAIL("wf must be one of 1,2,4,8,16,32");
+  if (cfg->max_batch < 1) ARG_FAIL("max_batch must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    tem_set_error("no CUDA device: transfer_em_b200 has no CPU fallback"); return TEM_ERR_CUDA;
+  }
+  TEM_CUDA(cudaSetDevice(cfg->device));
+  tem_handle* h = new tem_handle();
+  h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
+  h->keys_overridden = false; h->last_gen_net = 0; h->last_disc_net = 2;
+  h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
+  h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
+  long long off = 0;
+  for (int i = 0; i < 4; ++i) { h->nets[i].arena_off = off; off += (h->nets[i].count + 7) / 8 * 8; }
+  h->total_params = off; h->arena_elems = off + 16;
+  int d[12]; gen_dims(cfg->dimsize, d);
+  h->n = cfg->dimsize; h->outdim = d[11]; h->buffer = (h->n - h->outdim) / 2; h->dm = h->outdim;
+  int dd[9]; disc_dims(h->dm, h->nd, dd); h->dl = dd[8];
+  h->maxB = cfg->max_batch;
+  int rc = TEM_OK;
+  auto fail = [&](int s) { tem_destroy(h); return s; };
+  const size_t ab = (size_t)h->arena_elems * sizeof(float);
+  if ((rc = dev_alloc(h, (void**)&h->params, ab)) || (rc = dev_alloc(h, (void**)&h->grads, ab))) return fail(rc);
+  if ((rc = dev_alloc(h, (void**)&h->adam_m, ab)) || (rc = dev_alloc(h, (void**)&h->adam_v, ab))) return fail(rc);
+  h->loss_dev = h->grads + h->total_params;
+  cudaMemset(h->params, 0, ab); cudaMemset(h->grads, 0, ab); cudaMemset(h->adam_m, 0, ab); cudaMemset(h->adam_v, 0, ab);
+  for (int i = 0; i < 4; ++i) {   // N(0, 0.02) kernels, zero bias
+    const NetSpec& N = h->nets[i];
+    for (size_t li = 0; li < N.L.size(); ++li)
+      launch_init_normal(h->params + N.arena_off + N.L[li].w_off, N.L[li].w_count, cfg->seed * 1315423911ull + i * 1000 + li, 0.02f, 0);
+  }
+  const int B = h->maxB;
+  const int npass = cfg->train ? 7 : 1;
+  for (int i = 0; i < 7; ++i) h->gp[i].valid = false;
+  for (int i = 0; i < 5; ++i) h->dp[i].valid = false;
+  if (cfg->train) {
+    for (int i = 0; i < 6; ++i) if ((rc = alloc_gen_pass(h, h->gp[i], B, h->n))) return fail(rc);
+    for (int i = 0; i < 4; ++i) if ((rc = alloc_disc_pass(h, h->dp[i], B, h->dm))) return fail(rc);
+    for (int i = 0; i < 11; ++i) if ((rc = alloc_tensor(h, h->gdP[i], DT_BF16, B, d[i], h->nets[0].L[i].cout))) return fail(rc);
+    for (int i = 0; i < 8; ++i) if ((rc = alloc_tensor(h, h->ddP[i], DT_BF16, B, dd[i] > 0 ? dd[i] : 1, h->nets[2].L[i].cout))) return fail(rc);
+    long long osz = (long long)B * h->outdim * h->outdim * (h->nd == 3 ? h->outdim : 1);
+    for (int i = 0; i < 6; ++i) if ((rc = dev_alloc(h, (void**)&h->dOut[i], osz * 4))) return fail(rc);
+    long long lsz = (long long)B * h->dl * h->dl * (h->nd == 3 ? h->dl : 1);
+    for (int i = 0; i < 6; ++i) if ((rc = dev_alloc(h, (void**)&h->dlog[i], lsz * 4))) return fail(rc);
+  }
+  (void)npass;
+  if ((rc = alloc_gen_pass(h, h->gp[6], B, h->n))) return fail(rc);
+  if ((rc = alloc_disc_pass(h, h->dp[4], B, h->dm))) return fail(rc);
+  if ((rc = dev_alloc(h, (void**)&h->tile_origins, (size_t)B * 3 * sizeof(int)))) return fail(rc);
+  if ((rc = dev_alloc(h, (void**)&h->tile_index, (size_t)B * 3 * sizeof(int)))) return fail(rc);
+  h->h_tile_origins = h->h_tile_index = nullptr;
+  if (cudaDeviceSynchronize() != cudaSuccess) { tem_set_error("device sync failed after init"); return fail(TEM_ERR_CUDA); }
+  *out = h;
+  return TEM_OK;
+}
+
+extern "C" int tem_destroy(tem_handle* h) {
+  if (!h) return TEM_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);
+  if (h->h_tile_index) cudaFreeHost(h->h_tile_index);
+  delete h;
+  return TEM_OK;
+}
+
+extern "C" int tem_out_dim(const tem_handle* h, int32_t* outdimsize, int32_t* buffer) {
+  if (!h) ARG_FAIL("null handle");
+  if (outdimsize) *outdimsize = h->outdim; if (buffer) *buffer = h->buffer;
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t tem_param_count(const tem_handle* h, int net) {
+  if (!h || net < 0 || net > 3) { tem_set_error("bad net"); return TEM_ERR_ARG; }
+  return h->nets[net].count;
+}
+extern "C" int tem_num_variables(const tem_handle* h, int net) {
+  if (!h || net < 0 || net > 3) { tem_set_error("bad net"); return TEM_ERR_ARG; }
+  int n = 0; for (auto& L : h->nets[net].L) n += 1 + (L.bias ? 1 : 0);
+  return n;
+}
+extern "C" int tem_variable_info(const tem_handle* h, int net, int var, char name[32], int64_t* offset, int32_t* ndim, int64_t shape[6]) {
+  if (!h || net < 0 || net > 3) ARG_FAIL("bad net");
+  int idx = 0;
+  for (auto& L : h->nets[net].L) {
+    if (idx == var) {
+      if (name) snprintf(name, 32, "%s/kernel", L.name);
+      if (offset) *offset = L.w_off;
+      int nd = 0;
+      for (int i = 0; i < h->nd; ++i) shape[nd++] = L.k;
+      if (!L.transposed) { shape[nd++] = L.cin; shape[nd++] = L.cout; } else { shape[nd++] = L.cout; shape[nd++] = L.cin; }
+      if (ndim) *ndim = nd;
+      return TEM_OK;
+    }
+    ++idx;
+    if (L.bias) {
+      if (idx == var) {
+        if (name) snprintf(name, 32, "%s/bias", L.name);
+        if (offset) *offset = L.b_off;
+        shape[0] = L.cout; if (ndim) *ndim = 1;
+        return TEM_OK;
+      }
+      ++idx;
+    }
+  }
+  ARG_FAIL("variable index %d out of range", var);
+}
+static float* vec_ptr(tem_handle* h, int which) {
+  switch (which) { case 0: return h->params; case 1: return h->grads; case 2: return h->adam_m; case 3: return h->adam_v; }
+  return nullptr;
+}
+extern "C" int tem_get_vector(tem_handle* h, int net, int which, float* dst, void* stream) {
+  if (!h || net < 0 || net > 3 || !dst) ARG_FAIL("tem_get_vector: bad arguments");
+  float* base = vec_ptr(h, which); if (!base) ARG_FAIL("bad vector selector %d", which);
+  TEM_CUDA(cudaMemcpyAsync(dst, base + h->nets[net].arena_off, (size_t)h->nets[net].count * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+  TEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_set_vector(tem_handle* h, int net, int which, const float* src, void* stream) {
+  if (!h || net < 0 || net > 3 || !src) ARG_FAIL("tem_set_vector: bad arguments");
+  float* base = vec_ptr(h, which); if (!base) ARG_FAIL("bad vector selector %d", which);
+  TEM_CUDA(cudaMemcpyAsync(base + h->nets[net].arena_off, src, (size_t)h->nets[net].count * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+  TEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_get_step(const tem_handle* h, int64_t* step) { if (!h || !step) ARG_FAIL("null"); *step = h->step; return TEM_OK; }
+extern "C" int tem_set_step(tem_handle* h, int64_t step) { if (!h) ARG_FAIL("null"); h->step = step; return TEM_OK; }
+
+// ------------------------------------------------------------------------------------------
+// forward API
+// ------------------------------------------------------------------------------------------
+static int make_input(const tem_handle* h, const void* p, int dtype, int edge, int shift, const float* meanstd, InputRef& in) {
+  memset(&in, 0, sizeof(in));
+  in.p = p; in.dtype = dtype; spatial(h, edge, in.dims); axes(h, shift, 0, in.shift);
+  if (dtype == DT_U8) {
+    if (!meanstd) ARG_FAIL("uint8 input needs meanstd");
+    in.use_lut = 1; in.mean = meanstd[0]; in.stdv = meanstd[1];
+  } else if (dtype != DT_F32 && dtype != DT_BF16) ARG_FAIL("unsupported input dtype %d", dtype);
+  return TEM_OK;
+}
+
+extern "C" int tem_gen_forward(tem_handle* h, int net, const void* in, int in_dtype, const float* meanstd,
+                               int B, int n, uint32_t dropout_key, float* out, void* stream) {
+  if (!h || !in || !out) ARG_FAIL("tem_gen_forward: null argument");
+  if (net != TEM_NET_G && net != TEM_NET_F) ARG_FAIL("net must be a generator");
+  if (B < 1 || B > h->maxB) ARG_FAIL("batch %d exceeds max_batch %d", B, h->maxB);
+  if (n < 38 || n % 4 != 2 || n > h->n) ARG_FAIL("%d does not allow for valid convolutions (need n = 2 mod 4, 38 <= n <= dimsize)", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  InputRef ir; TEM_CHECK(make_input(h, in, in_dtype, n, 0, meanstd, ir));
+  uint32_t keys[2] = {0, 0};
+  if (dropout_key) { keys[0] = tem_hash32(dropout_key ^ 0x6b43a9b5u) | 1u; keys[1] = tem_hash32(dropout_key ^ 0x52dce729u) | 1u; }
+  GenPass& P = h->gp[6];
+  TEM_CHECK(gen_forward(h, net, P, ir, B, n, keys, st));
+  h->last_gen_net = net;
+  const long long cnt = (long long)B * P.a[11].per_sample();
+  TEM_CUDA(cudaMemcpyAsync(out, P.a[11].p, cnt * 4, cudaMemcpyDefault, st));
+  return TEM_OK;
+}
+
+extern "C" int tem_disc_out_dim(const tem_handle* h, int m, int32_t* l) {
+  if (!h || !l) ARG_FAIL("null");
+  int d[9]; disc_dims(m, h->nd, d); *l = d[8];
+  return TEM_OK;
+}
+
+extern "C" int tem_disc_forward(tem_handle* h, int net, const float* in, int B, int m, float* logits, void* stream) {
+  if (!h || !in || !logits) ARG_FAIL("tem_disc_forward: null argument");
+  if (net != TEM_NET_DX && net != TEM_NET_DY) ARG_FAIL("net must be a discriminator");
+  if (B < 1 || B > h->maxB) ARG_FAIL("batch %d exceeds max_batch %d", B, h->maxB);
+  if (m > h->dm) ARG_FAIL("discriminator input edge %d exceeds workspace (%d)", m, h->dm);
+  cudaStream_t st = (cudaStream_t)stream;
+  InputRef ir; TEM_CHECK(make_input(h, in, DT_F32, m, 0, nullptr, ir));
+  DiscPass& P = h->dp[4];
+  TEM_CHECK(disc_forward(h, net, P, ir, B, m, st));
+  h->last_disc_net = net;
+  TEM_CUDA(cudaMemcpyAsync(logits, P.a[8].p, (size_t)B * P.a[8].per_sample() * 4, cudaMemcpyDefault, st));
+  return TEM_OK;
+}
+
+extern "C" int tem_last_activation(tem_handle* h, int net, int layer, float* dst, int64_t* count, void* stream) {
+  if (!h || !count) ARG_FAIL("null");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Tensor* t = nullptr; int B = 0;
+  if (net == TEM_NET_G || net == TEM_NET_F) {
+    if (layer < 0 || layer > 11 || !h->gp[6].valid) ARG_FAIL("no such activation");
+    t = &h->gp[6].a[layer]; B = h->gp[6].B;
+  } else {
+    if (layer < 0 || layer > 8 || !h->dp[4].valid) ARG_FAIL("no such activation");
+    t = &h->dp[4].a[layer]; B = h->dp[4].B;
+  }
+  const long long cnt = (long long)B * t->per_sample();
+  *count = cnt;
+  if (!dst) return TEM_OK;
+  if (t->dtype == DT_F32) TEM_CUDA(cudaMemcpyAsync(dst, t->p, cnt * 4, cudaMemcpyDefault, st));
+  else TEM_CUDA(launch_cast_bf16_f32((const bf16*)t->p, dst, cnt, st));
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// train step (cgan.py:144-230)
+// ------------------------------------------------------------------------------------------
+__global__ void finalize_losses_kernel(const float* acc, float scale, float* out) {
+  // acc: [2] disc_y [3] disc_x [4] gen_g [5] gen_f [6] cycle [7] id_g [8] id_f ; out order of cgan.py:230
+  if (threadIdx.x == 0) {
+    const float gen_g = acc[4] * scale, gen_f = acc[5] * scale, cyc = acc[6] * scale;
+    out[0] = gen_g + cyc + acc[7] * scale;
+    out[1] = gen_f + cyc + acc[8] * scale;
+    out[2] = acc[2] * scale; out[3] = acc[3] * scale;
+    out[4] = gen_g; out[5] = gen_f; out[6] = cyc;
+  }
+}
+
+static uint32_t derive_key(uint64_t seed, uint64_t step, uint64_t pass, uint64_t layer) {
+  uint64_t k = seed * 0x9E3779B97F4A7C15ull + step * 0xD1B54A32D192ED03ull + pass * 0x94D049BB133111EBull + layer * 0xBF58476D1CE4E5B9ull;
+  k ^= k >> 31;
+  return tem_hash32((uint32_t)((k ^ (k >> 32)) & 0xFFFFFFFFu));
+}
+
+static int pair_loss(tem_handle* h, const InputRef& real, const float* gen, int B, int crop, float scale, float* loss_slot,
+                     float* grad, cudaStream_t st) {
+  PairLossArgs a; memset(&a, 0, sizeof(a));
+  a.a = view_of_input(real);
+  axes(h, h->buffer, 0, a.a.shift);            // generated voxel z <-> real voxel z + buffer
+  a.b = gen; a.B = B; spatial(h, h->outdim, a.N); axes(h, crop, 0, a.crop);
+  a.gamma = h->cfg.focal_gamma; a.scale = scale; a.mode = h->cfg.loss_mode == TEM_LOSS_FOCAL ? 0 : 1;
+  a.use_lut = real.use_lut; a.lut_mean = real.mean; a.lut_std = real.stdv;
+  a.loss_out = loss_slot; a.grad = grad;
+  TEM_CUDA(launch_pair_loss(a, st));
+  return TEM_OK;
+}
+
+static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, int in_dtype,
+                         const float* msx, const float* msy, int B, cudaStream_t st) {
+  if (!h->cfg.train) { tem_set_error("handle was created with train=0"); return TEM_ERR_STATE; }
+  if (!real_x || !real_y) ARG_FAIL("null input");
+  if (B < 1 || B > h->maxB) ARG_FAIL("batch %d exceeds max_batch %d", B, h->maxB);
+  const int n = h->n, buf = h->buffer, od = h->outdim;
+  InputRef rx, ry; TEM_CHECK(make_input(h, real_x, in_dtype, n, 0, msx, rx)); TEM_CHECK(make_input(h, real_y, in_dtype, n, 0, msy, ry));
+  // dropout keys for this step
+  uint32_t keys[12];
+  for (int p = 0; p < 6; ++p) for (int l = 0; l < 2; ++l) {
+    uint32_t k = 0;
+    if (h->keys_overridden) k = h->next_keys[p * 2 + l];
+    else if (h->cfg.dropout) k = derive_key(h->cfg.seed + 0x51ull * (uint64_t)h->rank, (uint64_t)h->step, p, l) | 1u;
+    keys[p * 2 + l] = k;
+  }
+  memcpy(h->next_keys, keys, sizeof(keys));
+  TEM_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)h->arena_elems * 4, st));
+  const int G = TEM_NET_G, F = TEM_NET_F, DX = TEM_NET_DX, DY = TEM_NET_DY;
+  GenPass* gp = h->gp; DiscPass* dp = h->dp;
+  // ---- forward (pass ids: 0 fake_y, 1 cycled_x, 2 fake_x, 3 cycled_y, 4 same_x, 5 same_y)
+  TEM_CHECK(gen_forward(h, G, gp[0], rx, B, n, keys + 0, st));                         // cgan.py:152
+  TEM_CHECK(gen_forward(h, F, gp[2], ry, B, n, keys + 4, st));                         // :167
+  InputRef fy, fx;                                                                     // ZeroPadding3D(buffer): :161,:170
+  TEM_CHECK(make_input(h, gp[0].a[11].p, DT_F32, od, -buf, nullptr, fy));
+  TEM_CHECK(make_input(h, gp[2].a[11].p, DT_F32, od, -buf, nullptr, fx));
+  TEM_CHECK(gen_forward(h, F, gp[1], fy, B, n, keys + 2, st));                         // :162
+  TEM_CHECK(gen_forward(h, G, gp[3], fx, B, n, keys + 6, st));                         // :171
+  TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, st));                         // :177
+  TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, st));                        // :181
+  InputRef rxc = rx, ryc = ry; axes(h, buf, 0, rxc.shift); axes(h, buf, 0, ryc.shift); // Cropping3D(buffer): :179,:183
+  InputRef fyd, fxd;
+  TEM_CHECK(make_input(h, gp[0].a[11].p, DT_F32, od, 0, nullptr, fyd));
+  TEM_CHECK(make_input(h, gp[2].a[11].p, DT_F32, od, 0, nullptr, fxd));
+  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, st));                               // :185
+  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, st));                               // :186
+  TEM_CHECK(disc_forward(h, DX, dp[2], fxd, B, od, st));                               // :188
+  TEM_CHECK(disc_forward(h, DY, dp[3], fyd, B, od, st));                               // :189
+  // ---- losses (accumulators live behind the gradient arena so one all-reduce covers both)
+  float* LS = h->loss_dev;
+  const long long nl = (long long)B * dp[0].a[8].per_sample();
+  const bool focal = h->cfg.loss_mode == TEM_LOSS_FOCAL;
+  const int lm = focal ? 0 : 1;
+  const float gamma = h->cfg.focal_gamma;
+  const float s_gen = focal ? 2.f : 1.f, s_disc = focal ? 1.f : 0.5f;
+  const float s_cyc = focal ? 4.f : 1.f, s_id = focal ? 2.f : 0.5f;
+  const float* lg_dxr = (const float*)dp[0].a[8].p; const float* lg_dyr = (const float*)dp[1].a[8].p;
+  const float* lg_dxf = (const float*)dp[2].a[8].p; const float* lg_dyf = (const float*)dp[3].a[8].p;
+  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 1.f, gamma, s_gen, lm, LS + 4, h->dlog[0], st));    // gen_g  :192
+  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 1.f, gamma, s_gen, lm, LS + 5, h->dlog[1], st));    // gen_f  :193
+  TEM_CUDA(launch_focal_logits(lg_dyr, nl, 1.f, gamma, s_disc, lm, LS + 2, h->dlog[2], st));   // disc_y :203
+  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 0.f, gamma, s_disc, lm, LS + 2, h->dlog[3], st));
+  TEM_CUDA(launch_focal_logits(lg_dxr, nl, 1.f, gamma, s_disc, lm, LS + 3, h->dlog[4], st));   // disc_x :202
+  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 0.f, gamma, s_disc, lm, LS + 3, h->dlog[5], st));
+  TEM_CHECK(pair_loss(h, rx, (const float*)gp[1].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[1], st));   // cycle x :196
+  TEM_CHECK(pair_loss(h, ry, (const float*)gp[3].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[3], st));   // cycle y
+  TEM_CHECK(pair_loss(h, rx, (const float*)gp[4].a[11].p, B, 0, s_id, LS + 8, h->dOut[4], st));      // identity f :200
+  TEM_CHECK(pair_loss(h, ry, (const float*)gp[5].a[11].p, B, 0, s_id, LS + 7, h->dOut[5], st));      // identity g :199
+  // ---- backward
+  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[0], false, h->dOut[0], st));   // d gen_g / d fake_y
+  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[1], false, h->dOut[2], st));   // d gen_f / d fake_x
+  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, st));       // disc_y wrt D_y   :214
+  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, st));
+  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, st));       // disc_x wrt D_x   :212
+  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, st));
+  TEM_CHECK(gen_backward(h, F, gp[1], h->dOut[1], h->dOut[0], st));            // cycled_x -> F, and into fake_y
+  TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], st));            // cycled_y -> G, and into fake_x
+  TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, st));
+  TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, st));
+  TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, st));
+  TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, st));
+  return TEM_OK;
+}
+
+static int write_losses(tem_handle* h, float scale, float* losses_out, cudaStream_t st) {
+  if (!losses_out) return TEM_OK;
+  finalize_losses_kernel<<<1, 32, 0, st>>>(h->loss_dev, scale, h->loss_dev + 9);
+  TEM_CUDA(cudaGetLastError());
+  TEM_CUDA(cudaMemcpyAsync(losses_out, h->loss_dev + 9, 7 * sizeof(float), cudaMemcpyDefault, st));
+  return TEM_OK;
+}
+
+static int apply_adam(tem_handle* h, float gscale, cudaStream_t st) {
+  h->step += 1;
+  const double b1 = h->cfg.beta1, b2 = h->cfg.beta2;
+  const float lr_t = (float)(h->cfg.lr * sqrt(1.0 - pow(b2, (double)h->step)) / (1.0 - pow(b1, (double)h->step)));
+  TEM_CUDA(launch_adam(h->params, h->grads, h->adam_m, h->adam_v, h->total_params, lr_t, h->cfg.beta1, h->cfg.beta2,
+                       h->cfg.eps, gscale, st));
+  return TEM_OK;
+}
+
+extern "C" int tem_train_grads(tem_handle* h, const void* real_x, const void* real_y, int in_dtype,
+                               const float* msx, const float* msy, int B, float* losses_out, void* stream) {
+  if (!h) ARG_FAIL("null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  TEM_CHECK(train_fwd_bwd(h, real_x, real_y, in_dtype, msx, msy, B, st));
+  return write_losses(h, 1.f, losses_out, st);
+}
+
+extern "C" int tem_apply_adam(tem_handle* h, float grad_scale, void* stream) {
+  if (!h) ARG_FAIL("null handle");
+  return apply_adam(h, grad_scale, (cudaStream_t)stream);
+}
+
+extern "C" int tem_train_step(tem_handle* h, const void* real_x, const void* real_y, int in_dtype,
+                              const float* msx, const float* msy, int B, float* losses_out, void* stream) {
+  if (!h) ARG_FAIL("null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  TEM_CHECK(train_fwd_bwd(h, real_x, real_y, in_dtype, msx, msy, B, st));
+  float scale = 1.f;
+  if (h->comm && h->world > 1) {
+    // per-replica losses are means over the local batch: the global-batch mean is the rank average (cgan.py:8-11)
+    TEM_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->arena_elems, kNcclFloat32, kNcclSum, h->comm, st));
+    scale = 1.f / (float)h->world;
+  }
+  TEM_CHECK(write_losses(h, scale, losses_out, st));
+  TEM_CHECK(apply_adam(h, scale, st));
+  h->keys_overridden = false;
+  return TEM_OK;
+}
+
+extern "C" int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* count, void* stream) {
+  if (!h || pass < 0 || pass > 5 || !count) ARG_FAIL("bad arguments");
+  if (!h->cfg.train || !h->gp[pass].valid) { tem_set_error("no train step has run"); return TEM_ERR_STATE; }
+  const long long cnt = (long long)h->gp[pass].B * h->gp[pass].a[11].per_sample();
+  *count = cnt;
+  if (dst) TEM_CUDA(cudaMemcpyAsync(dst, h->gp[pass].a[11].p, cnt * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_set_dropout_keys(tem_handle* h, const uint32_t keys[12]) {
+  if (!h || !keys) ARG_FAIL("null");
+  memcpy(h->next_keys, keys, sizeof(h->next_keys)); h->keys_overridden = true;
+  return TEM_OK;
+}
+extern "C" int tem_get_dropout_keys(tem_handle* h, uint32_t keys[12]) {
+  if (!h || !keys) ARG_FAIL("null");
+  memcpy(keys, h->next_keys, sizeof(h->next_keys));
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tiled inference (transfer_em/utils.py:41-130)
+// ------------------------------------------------------------------------------------------
+extern "C" int tem_predict_volume(tem_handle* h, int net, const uint8_t* vol, const int64_t vd[3],
+                                  const int64_t start[3], const int64_t size[3],
+                                  const float msx[2], const float msy[2], int outdimsize, int buffer,
+                                  int tz_begin, int tz_end, uint8_t* out, uint8_t* in_out, void* stream) {
+  if (!h || !vol || !vd || !start || !size || !msx || !msy || !out) ARG_FAIL("tem_predict_volume: null argument");
+  if (h->nd != 3) { tem_set_error("predict_ng_cube is 3-D only (utils.py:78-84)"); return TEM_ERR_UNSUPPORTED; }
+  if (net != TEM_NET_G && net != TEM_NET_F) ARG_FAIL("net must be a generator");
+  cudaStream_t st = (cudaStream_t)stream;
+  // utils.py:68-75 (literal arithmetic)
+  int od = outdimsize > 0 ? outdimsize : h->outdim;
+  int buf = buffer >= 0 ? buffer : h->buffer;
+  int tpad = 0;
+  if ((od / 6) != 0) { int diff = od % 6; od -= diff; tpad = diff / 2; buf += tpad; }
+  const int tsz = od + 2 * buf;
+  if (tsz > h->n || tsz % 4 != 2 || tsz - 34 != od + 2 * tpad) ARG_FAIL("tile size %d is not servable by this model (dimsize %d)", tsz, h->n);
+  if (size[0] <= 0 || size[1] <= 0 || size[2] <= 0) ARG_FAIL("empty request");
+  const long long nx = (size[0] + od - 1) / od, ny = (size[1] + od - 1) / od, nz = (size[2] + od - 1) / od;
+  if (tz_begin < 0) tz_begin = 0; if (tz_end < 0 || tz_end > nz) tz_end = (int)nz;
+  if (!h->h_tile_origins) {
+    TEM_CUDA(cudaMallocHost((void**)&h->h_tile_origins, (size_t)h->maxB * 3 * sizeof(int) * 2));
+    h->h_tile_index = h->h_tile_origins + (size_t)h->maxB * 3;
+  }
+  const int T = h->maxB;
+  GenPass& P = h->gp[6];
+  // tile order of the reference: x outer, y, z inner (utils.py:78-84); restricted to the z slab
+  long long done = 0;
+  const long long total = nx * ny * (tz_end - tz_begin);
+  InputRef ir; memset(&ir, 0, sizeof(ir));
+  ir.p = vol; ir.dtype = DT_U8; set3(ir.dims, (int)vd[0], (int)vd[1], (int)vd[2]);
+  ir.origins = h->tile_origins; ir.use_lut = 1; ir.mean = msx[0]; ir.stdv = msx[1];
+  if (vd[0] > 2147483647LL || vd[1] > 2147483647LL || vd[2] > 2147483647LL) ARG_FAIL("volume too large");
+  while (done < total) {
+    const int nb = (int)std::min<long long>(T, total - done);
+    // the previous batch must have consumed the staging buffers before they are rewritten
+    TEM_CUDA(cudaStreamSynchronize(st));
+    for (int t = 0; t < nb; ++t) {
+      long long id = done + t;
+      const long long zi = tz_begin + id % (tz_end - tz_begin); id /= (tz_end - tz_begin);
+      const long long yi = id % ny; const long long xi = id / ny;
+      const long long x0 = start[0] + xi * od, y0 = start[1] + yi * od, z0 = start[2] + zi * od;
+      h->h_tile_origins[t * 3 + 0] = (int)(z0 - buf); h->h_tile_origins[t * 3 + 1] = (int)(y0 - buf); h->h_tile_origins[t * 3 + 2] = (int)(x0 - buf);
+      h->h_tile_index[t * 3 + 0] = (int)(xi * od); h->h_tile_index[t * 3 + 1] = (int)(yi * od); h->h_tile_index[t * 3 + 2] = (int)(zi * od);
+    }
+    TEM_CUDA(cudaMemcpyAsync(h->tile_origins, h->h_tile_origins, (size_t)nb * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    TEM_CUDA(cudaMemcpyAsync(h->tile_index, h->h_tile_index, (size_t)nb * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    TEM_CHECK(gen_forward(h, net, P, ir, nb, tsz, nullptr, st));
+    StitchArgs sa; memset(&sa, 0, sizeof(sa));
+    sa.y = (const float*)P.a[11].p; sa.index = h->tile_index; sa.T = nb; sa.ydim = od + 2 * tpad; sa.tpad = tpad; sa.od = od;
+    sa.mean = msy[0]; sa.stdv = msy[1]; sa.out = out; sa.OZ = size[2]; sa.OY = size[1]; sa.OX = size[0];
+    TEM_CUDA(launch_stitch_u8(sa, st));
+    if (in_out) {
+      FetchInArgs fa; memset(&fa, 0, sizeof(fa));
+      fa.vol = vol; fa.VZ = vd[0]; fa.VY = vd[1]; fa.VX = vd[2]; fa.origins = h->tile_origins; fa.index = h->tile_index;
+      fa.T = nb; fa.buf = buf; fa.od = od; fa.mean = msx[0]; fa.stdv = msx[1]; fa.out = in_out; fa.OZ = size[2]; fa.OY = size[1]; fa.OX = size[0];
+      TEM_CUDA(launch_fetch_input_u8(fa, st));
+    }
+    done += nb;
+  }
+  h->last_gen_net = net;
+  return TEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise + per-op entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int tem_standardize_u8(const uint8_t* in, float* out, int64_t n, const float ms[2], void* stream) {
+  if (!in || !out || !ms) ARG_FAIL("null");
+  TEM_CUDA(launch_standardize_u8(in, out, n, ms[0], ms[1], (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_unstandardize_to_u8(const float* in, uint8_t* out, int64_t n, const float ms[2], void* stream) {
+  if (!in || !out || !ms) ARG_FAIL("null");
+  TEM_CUDA(launch_unstandardize_u8(in, out, n, ms[0], ms[1], (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_focal_logits(const float* logits, int64_t n, float target, float gamma, float scale,
+                                float* loss_out, float* grad, void* stream) {
+  if (!logits || n <= 0) ARG_FAIL("bad arguments");
+  TEM_CUDA(launch_focal_logits(logits, n, target, gamma, scale, 0, loss_out, grad, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_focal_probs(const float* a, const float* b, int64_t n, float gamma, float scale,
+                               float* loss_out, float* grad_b, void* stream) {
+  if (!a || !b || n <= 0) ARG_FAIL("bad arguments");
+  PairLossArgs p; memset(&p, 0, sizeof(p));
+  p.a.p = a; p.a.dtype = DT_F32; p.a.Z = 1; p.a.Y = 1; p.a.X = (int)n; p.a.C = 1; p.a.bstride = n;
+  p.b = b; p.B = 1; p.N[0] = 1; p.N[1] = 1; p.N[2] = (int)n; p.gamma = gamma; p.scale = scale; p.mode = 0;
+  p.loss_out = loss_out; p.grad = grad_b;
+  TEM_CUDA(launch_pair_loss(p, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_adam(float* p, const float* g, float* m, float* v, int64_t n, int64_t step,
+                        float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || step < 1) ARG_FAIL("bad arguments");
+  const float lr_t = (float)(lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  TEM_CUDA(launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_dropout_mask(uint32_t key, float* out, int64_t n, void* stream) {
+  if (!out) ARG_FAIL("null");
+  TEM_CUDA(launch_dropout_mask(key, out, n, (cudaStream_t)stream));
+  return TEM_OK;
+}
+
+// per-op conv entry points: a throw-away one-layer "network" over caller-owned buffers
+static int desc_layer(const tem_conv_desc* d, tem_handle& fake, LayerSpec& L, int in_d[3], int out_d[3]) {
+  if (!d) ARG_FAIL("null descriptor");
+  memset(&fake, 0, sizeof(tem_config));   // only nd is used by the helpers
+  const bool is3 = !(d->in_dims[0] == 1 && d->k[0] == 1);
+  fake.nd = is3 ? 3 : 2;
+  if (d->k[1] != d->k[2] || (is3 && d->k[0] != d->k[1])) ARG_FAIL("kernel must be isotropic");
+  if (d->stride[1] != d->stride[2]) ARG_FAIL("stride must be isotropic");
+  L = mk("op", d->transposed, d->k[1], d->stride[1], d->cin, d->cout, d->slope, d->dropout_key != 0, 0);
+  L.w_off = 0; L.b_off = 0;
+  for (int i = 0; i < 3; ++i) {
+    in_d[i] = d->in_dims[i];
+    const int k = (i == 0 && !is3) ? 1 : L.k, s = (i == 0 && !is3) ? 1 : L.stride;
+    out_d[i] = d->transposed ? in_d[i] * s : (in_d[i] - k) / s + 1;
+    if (out_d[i] < 1) ARG_FAIL("input too small for the kernel");
+  }
+  if (d->transposed && !(L.k == 4 && L.stride == 2)) ARG_FAIL("transposed conv supports k=4, s=2 (models/utils.py:129-130)");
+  return TEM_OK;
+}
+
+extern "C" int tem_conv_forward(const tem_conv_desc* d, const void* in, const float* w, const float* bias,
+                                void* out, int32_t out_dims[3], void* stream) {
+  tem_handle* fk = new tem_handle(); LayerSpec L; int id[3], od[3];
+  int rc = desc_layer(d, *fk, L, id, od);
+  if (rc == TEM_OK) {
+    if (out_dims) for (int i = 0; i < 3; ++i) out_dims[i] = od[i];
+    if (in && out && w) {
+      Tensor tin; tin.p = (void*)in; tin.dtype = d->in_dtype; set3(tin.d, id[0], id[1], id[2]); tin.C = d->cin;
+      Tensor tout; tout.p = out; tout.dtype = d->out_dtype; set3(tout.d, od[0], od[1], od[2]); tout.C = d->cout;
+      // bias is addressed through the net-relative offset: emulate with a tiny trick (bias pointer relative to w)
+      L.bias = bias ? 1 : 0; L.b_off = bias ? (bias - w) : 0;
+      rc = run_forward(fk, L, w, view_of(tin), d->cin, nullptr, 0, tout, d->B, d->dropout_key,
+                       d->in_dtype == DT_U8, d->meanstd[0], d->meanstd[1], (cudaStream_t)stream);
+    }
+  }
+  delete fk;
+  return rc;
+}
+
+extern "C" int tem_conv_dgrad(const tem_conv_desc* d, const void* dy, int dy_dtype, const float* w,
+                              const void* x_act, float x_slope, void* dx, int dx_dtype, void* stream) {
+  tem_handle* fk = new tem_handle(); LayerSpec L; int id[3], od[3];
+  int rc = desc_layer(d, *fk, L, id, od);
+  if (rc == TEM_OK) {
+    if (!dy || !w || !dx) { tem_set_error("null argument"); rc = TEM_ERR_ARG; }
+    else {
+      Tensor tdy; tdy.p = (void*)dy; tdy.dtype = dy_dtype; set3(tdy.d, od[0], od[1], od[2]); tdy.C = d->cout;
+      Tensor tdx; tdx.p = dx; tdx.dtype = dx_dtype; set3(tdx.d, id[0], id[1], id[2]); tdx.C = d->cin;
+      Tensor tref; tref.p = (void*)x_act; tref.dtype = DT_BF16; set3(tref.d, id[0], id[1], id[2]); tref.C = d->cin;
+      rc = run_dgrad(fk, L, w, tdy, 0, d->cin, tdx, 0, nullptr, tdx.d, nullptr, x_act ? &tref : nullptr, nullptr, x_slope,
+                     0, 0, d->B, (cudaStream_t)stream);
+    }
+  }
+  delete fk;
+  return rc;
+}
+
+extern "C" int tem_conv_wgrad(const tem_conv_desc* d, const void* x, const void* dy, int dy_dtype, float* dw, void* stream) {
+  tem_handle* fk = new tem_handle(); LayerSpec L; int id[3], od[3];
+  int rc = desc_layer(d, *fk, L, id, od);
+  if (rc == TEM_OK) {
+    if (!x || !dy || !dw) { tem_set_error("null argument"); rc = TEM_ERR_ARG; }
+    else {
+      Tensor tx; tx.p = (void*)x; tx.dtype = d->in_dtype; set3(tx.d, id[0], id[1], id[2]); tx.C = d->cin;
+      Tensor tdy; tdy.p = (void*)dy; tdy.dtype = dy_dtype; set3(tdy.d, od[0], od[1], od[2]); tdy.C = d->cout;
+      rc = run_wgrad(fk, L, dw, view_of(tx), 0, d->cin, tdy, d->B, d->in_dtype == DT_U8, d->meanstd[0], d->meanstd[1],
+                     (cudaStream_t)stream);
+    }
+  }
+  delete fk;
+  return rc;
+}

@@ -1,0 +1,97 @@
+// Host-side runtime structures of libtem_b200: network tables, workspaces, pass executors.
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/transfer_em_b200.h"
+#include "tem_kernels.cuh"
+
+struct LayerSpec {
+  char name[8];
+  int transposed;     // 0 conv, 1 convT
+  int k, stride;
+  int cin, cout;
+  float slope;        // activation slope (1 = linear)
+  int dropout, bias;
+  long long w_off, b_off;   // element offsets inside the net's flat parameter vector
+  long long w_count;
+};
+
+struct NetSpec {
+  int is_gen;
+  std::vector<LayerSpec> L;
+  long long count;        // parameters in this net
+  long long arena_off;    // offset of this net in the shared arena
+};
+
+struct Tensor {          // dense [B, d0, d1, d2, C]
+  void* p; int dtype; int d[3]; int C;
+  long long per_sample() const { return (long long)d[0] * d[1] * d[2] * C; }
+};
+
+struct InputRef {        // first-layer input of a pass
+  const void* p; int dtype;
+  int dims[3];           // tensor dims
+  int shift[3];          // logical -> tensor coordinate
+  const int* origins;    // per-sample origins (tiled inference)
+  int use_lut; float mean, stdv;
+};
+
+struct GenPass {
+  Tensor a[12];          // a[0..10] bf16 activations, a[11] fp32 output
+  InputRef in;
+  uint32_t keys[2];      // dropout keys of g6, g9 (0 = off)
+  int B, n;
+  bool valid;
+};
+
+struct DiscPass {
+  Tensor a[9];           // a[0..7] bf16, a[8] fp32 logits
+  InputRef in;
+  int B, m;
+  bool valid;
+};
+
+struct NcclApi;
+
+struct tem_handle {
+  tem_config cfg;
+  NetSpec nets[4];
+  long long total_params;      // all four nets
+  long long arena_elems;       // total_params + 16 loss slots (all-reduced together)
+  float *params, *grads, *adam_m, *adam_v;
+  float* loss_dev;             // = grads + total_params  (16 floats)
+  int64_t step;
+  int nd;                      // 3 or 2
+  int n, outdim, buffer;       // generator geometry
+  int dm, dl;                  // discriminator input / logit edge
+  int maxB;
+  // workspaces
+  GenPass gp[7];               // 0..5 train passes, 6 inference / API pass
+  DiscPass dp[5];              // 0..3 train passes (DxR, DyR, DxF, DyF), 4 API pass
+  Tensor gdP[11];              // generator backward scratch (bf16), shared by all passes
+  Tensor ddP[8];               // discriminator backward scratch
+  float* dOut[6];              // gradient w.r.t. each generator pass output (fp32)
+  float* dlog[6];              // logit gradients: gen_y, gen_x, dyr, dyf, dxr, dxf
+  int* tile_origins; int* tile_index;   // device, maxB*3 each
+  int* h_tile_origins; int* h_tile_index;   // pinned host staging
+  uint32_t next_keys[12]; bool keys_overridden;
+  // communicator
+  void* comm; int rank, world;
+  std::vector<void*> allocs;
+  int last_gen_net, last_disc_net;
+};
+
+void tem_set_error(const char* fmt, ...);
+#define TEM_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      tem_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), cudaGetErrorString(_e)); \
+      return TEM_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+#define TEM_CHECK(expr)                    \
+  do {                                     \
+    int _s = (expr);                       \
+    if (_s != TEM_OK) return _s;           \
+  } while (0)
