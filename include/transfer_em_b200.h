@@ -111,6 +111,9 @@ int tem_train_grads(tem_handle* h, const void* real_x, const void* real_y, int i
 int tem_apply_adam(tem_handle* h, float grad_scale, void* stream);
 /* Output of generator pass p of the last train step (0 fake_y,1 cycled_x,2 fake_x,3 cycled_y,4 same_x,5 same_y). */
 int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* count, void* stream);
+/* debug/test: gradient w.r.t. the pre-activation of layer `layer` left in the backward scratch by the LAST
+ * backward pass of a train step (generator: the same_y pass, cgan.py:181; discriminator: D_x on fake_x). */
+int tem_debug_backward_scratch(tem_handle* h, int is_gen, int layer, float* dst, int64_t* count, void* stream);
 /* Override the dropout keys of the next train step (6 passes x 2 layers); 0 disables a mask. */
 int tem_set_dropout_keys(tem_handle* h, const uint32_t keys[12]);
 int tem_get_dropout_keys(tem_handle* h, uint32_t keys[12]);

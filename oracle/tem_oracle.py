@@ -270,7 +270,8 @@ def generator_forward(params: Sequence[torch.Tensor], x_cl: torch.Tensor, wf: in
                       is3d: bool = True, training: bool = False,
                       masks: Optional[Dict[str, torch.Tensor]] = None,
                       quant: Quant = None, qweights: bool = False,
-                      acts: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                      acts: Optional[Dict[str, torch.Tensor]] = None,
+                      graph_acts: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
     """generator.py:22-117.  x_cl: [B,(Z,)Y,X,1].  masks: {'g6','g9'} keep-masks in
     channels-last layout.  quant: applied to every stored activation except the
     final linear output (mimics bf16 storage); qweights: bf16-round the kernels.
@@ -292,6 +293,10 @@ def generator_forward(params: Sequence[torch.Tensor], x_cl: torch.Tensor, wf: in
             y = q(y)
         if acts is not None:
             acts[L.name] = _to_cl(y)
+        if graph_acts is not None:
+            if y.requires_grad:
+                y.retain_grad()
+            graph_acts[L.name] = y          # NC.. tensor inside the autograd graph
         return y
 
     a0 = run(0, x)
@@ -424,7 +429,8 @@ def train_step_grads(P: Dict[str, List[np.ndarray]], real_x: np.ndarray, real_y:
                      masks: Optional[Dict[str, Dict[str, np.ndarray]]] = None,
                      loss_mode: str = 'focal', dtype=torch.float64, literal: bool = False,
                      quant: Quant = None, qweights: bool = False,
-                     keep_outputs: bool = False) -> StepResult:
+                     keep_outputs: bool = False,
+                     override_fakes: Optional[Dict[str, np.ndarray]] = None) -> StepResult:
     """Forward + gradients of cgan.py:148-215.  P = {'g','f','dx','dy'} parameter lists.
 
     masks: {pass_name: {'g6': keep, 'g9': keep}} for pass_name in
@@ -460,11 +466,18 @@ def train_step_grads(P: Dict[str, List[np.ndarray]], real_x: np.ndarray, real_y:
     def Dy(x):
         return discriminator_forward(T['dy'], x, wf, is3d, quant=quant, qweights=qweights)
 
-    fake_y = G(rx, 'g_realx')                            # cgan.py:152
+    def subst(name, t):
+        # test hook: evaluate the downstream graph at externally supplied values of a fake (straight-through
+        # for the gradient) so that both implementations see bit-identical second-pass inputs
+        if override_fakes and name in override_fakes:
+            return t + (torch.tensor(override_fakes[name], dtype=dtype) - t).detach()
+        return t
+
+    fake_y = subst('fake_y', G(rx, 'g_realx'))           # cgan.py:152
     cycled_x = Fn(pad_cl(fake_y, buf), 'f_fakey')        # :161-162
     cycled_x_c = crop_cl(cycled_x, buf)                  # :163
     rx_c2 = crop_cl(rx, 2 * buf)                         # :165
-    fake_x = Fn(ry, 'f_realy')                           # :167
+    fake_x = subst('fake_x', Fn(ry, 'f_realy'))          # :167
     cycled_y = G(pad_cl(fake_x, buf), 'g_fakex')         # :170-171
     cycled_y_c = crop_cl(cycled_y, buf)
     ry_c2 = crop_cl(ry, 2 * buf)
@@ -531,11 +544,12 @@ class OracleEM2EM:
     """Minimal CPU EM2EM (cgan.py:32-293) used for loss-curve parity and the CPU baseline."""
 
     def __init__(self, dimsize=74, is3d=True, wf=8, focal_gamma=2.0, seed=0, dtype=np.float32,
-                 loss_mode='focal'):
+                 loss_mode='focal', quant: Quant = None):
         if dimsize < 74:
             raise RuntimeError("minimum dimension allowed is 74")      # cgan.py:52-53
         rng = np.random.default_rng(seed)
         self.is3d, self.wf, self.gamma, self.dtype, self.loss_mode = is3d, wf, focal_gamma, dtype, loss_mode
+        self.quant = quant
         self.layers = {'g': generator_layers(wf), 'f': generator_layers(wf),
                        'dx': discriminator_layers(wf, is3d), 'dy': discriminator_layers(wf, is3d)}
         self.P = {k: init_params(self.layers[k], is3d, rng, dtype) for k in ('g', 'f', 'dx', 'dy')}
@@ -548,7 +562,7 @@ class OracleEM2EM:
     def train_step(self, real_x, real_y, masks=None):
         tdt = torch.float64 if self.dtype == np.float64 else torch.float32
         r = train_step_grads(self.P, real_x, real_y, self.wf, self.is3d, self.gamma, masks,
-                             self.loss_mode, dtype=tdt)
+                             self.loss_mode, dtype=tdt, quant=self.quant)
         self.t += 1
         for k in self.P:
             for i in range(len(self.P[k])):

@@ -56,6 +56,7 @@ _SIGS = {
     "tem_train_grads": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, _P, _P]),
     "tem_apply_adam": (C.c_int, [_P, C.c_float, _P]),
     "tem_train_output": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_int64), _P]),
+    "tem_debug_backward_scratch": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int64), _P]),
     "tem_set_dropout_keys": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "tem_get_dropout_keys": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "tem_predict_volume": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -506,8 +506,7 @@ extern "C" int tem_destroy(tem_handle* h) {
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);
-  if (h->h_tile_index) cudaFreeHost(h->h_tile_index);
+  if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);   // h_tile_index lives in the same allocation
   delete h;
   return TEM_OK;
 }
@@ -806,6 +805,17 @@ extern "C" int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* co
   const long long cnt = (long long)h->gp[pass].B * h->gp[pass].a[11].per_sample();
   *count = cnt;
   if (dst) TEM_CUDA(cudaMemcpyAsync(dst, h->gp[pass].a[11].p, cnt * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_debug_backward_scratch(tem_handle* h, int is_gen, int layer, float* dst, int64_t* count, void* stream) {
+  if (!h || !count || !h->cfg.train) ARG_FAIL("bad arguments");
+  if (layer < 0 || layer >= (is_gen ? 11 : 8)) ARG_FAIL("bad layer");
+  Tensor t = is_gen ? h->gdP[layer] : h->ddP[layer];
+  const int B = is_gen ? h->gp[5].B : h->dp[2].B;
+  if (is_gen) { int d[12]; gen_dims(h->n, d); spatial(h, d[layer], t.d); }
+  else { int d[9]; disc_dims(h->dm, h->nd, d); spatial(h, d[layer] > 0 ? d[layer] : 1, t.d); }
+  *count = (long long)B * t.per_sample();
+  if (dst) TEM_CUDA(launch_cast_bf16_f32((const bf16*)t.p, dst, *count, (cudaStream_t)stream));
   return TEM_OK;
 }
 extern "C" int tem_set_dropout_keys(tem_handle* h, const uint32_t keys[12]) {

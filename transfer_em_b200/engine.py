@@ -204,6 +204,13 @@ class Engine:
         nd = 3 if self.is3d else 2
         return out.cpu().numpy().reshape((-1,) + (self.outdimsize,) * nd + (1,))
 
+    def debug_backward_scratch(self, is_gen, layer):
+        cnt = C.c_int64()
+        check(self._lib.tem_debug_backward_scratch(self._h, int(is_gen), layer, None, C.byref(cnt), _stream()))
+        out = torch.empty(cnt.value, dtype=torch.float32, device=self.device)
+        check(self._lib.tem_debug_backward_scratch(self._h, int(is_gen), layer, C.c_void_p(out.data_ptr()), C.byref(cnt), _stream()))
+        return out.cpu().numpy()
+
     def set_dropout_keys(self, keys):
         arr = (C.c_uint32 * 12)(*[int(k) for k in keys])
         check(self._lib.tem_set_dropout_keys(self._h, arr))
