@@ -136,6 +136,14 @@ int tem_comm_world(const tem_handle* h, int* rank, int* world);
 /* broadcast rank 0's parameters + optimizer state to all ranks */
 int tem_comm_sync_params(tem_handle* h, void* stream);
 
+/* ---- measurement hooks (bench.py) ---- */
+/* number of kernels this library has launched in this process */
+uint64_t tem_launch_count(void);
+/* bracket every convolution launch with CUDA events on its stream, aggregated by "<layer>.<fwd|dgrad|wgrad>" */
+int tem_profile_enable(tem_handle* h, int on);
+/* synchronises, then writes one line per tag: "tag count total_ms algorithmic_bytes_per_launch flops_per_launch" */
+int tem_profile_report(tem_handle* h, char* buf, int64_t buflen);
+
 /* ---- element-wise conventions, exposed for bit-exact tests ---- */
 /* datasets.py:193-202 + 157-163 */
 int tem_standardize_u8(const uint8_t* in, float* out, int64_t n, const float meanstd[2], void* stream);

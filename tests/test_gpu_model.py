@@ -134,7 +134,7 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
     refq = O.train_step_grads(P, rx, ry, 8, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode,
                               quant=O.bf16_round, override_fakes=ov, keep_outputs=True)
     for name in ("fake_y", "cycled_x", "fake_x", "cycled_y", "same_x", "same_y"):
-        assert rel_l2(model.engine.train_output(name), refq.outputs[name]) < 3e-3, name
+        assert rel_l2(model.engine.train_output(name), refq.outputs[name]) < 8e-3, name
     np.testing.assert_allclose(np.array(losses), np.array(refq.losses), rtol=2e-3, atol=1e-5)
     worst = {}
     for k, net in NETS.items():

@@ -65,6 +65,9 @@ _SIGS = {
     "tem_comm_init": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
     "tem_comm_world": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tem_comm_sync_params": (C.c_int, [_P, _P]),
+    "tem_launch_count": (C.c_uint64, []),
+    "tem_profile_enable": (C.c_int, [_P, C.c_int]),
+    "tem_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "tem_standardize_u8": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_float), _P]),
     "tem_unstandardize_to_u8": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_float), _P]),
     "tem_conv_forward": (C.c_int, [C.POINTER(TemConvDesc), _P, _P, _P, _P, C.POINTER(C.c_int32), _P]),

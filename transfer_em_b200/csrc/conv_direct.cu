@@ -12,6 +12,7 @@
 // memory-bound and never go to tensor cores).  The tcgen05 implicit-GEMM kernels (conv_tc.cu) take over
 // the channel-heavy 3x3x3 layers when the shape allows.
 #include "tem_kernels.cuh"
+extern unsigned long long g_tem_launches;
 
 namespace {
 
@@ -377,7 +378,7 @@ cudaError_t launch_conv_t(const ConvArgs& a, cudaStream_t st) {
   int ncls = 1;
   if (a.form == 1) ncls = a.stride[0] * a.stride[1] * a.stride[2];
   dim3 grid((unsigned)((a.nvox + kThreads * kVPT - 1) / (kThreads * kVPT)), (a.Cout + CO_T - 1) / CO_T, ncls);
-  conv_direct_kernel<CO_T, CI_V><<<grid, kThreads, smem, st>>>(a);
+  conv_direct_kernel<CO_T, CI_V><<<grid, kThreads, smem, st>>>(a); ++g_tem_launches;
   return cudaGetLastError();
 }
 
@@ -436,10 +437,11 @@ cudaError_t launch_wgrad_direct(const WgradArgs& a_in, cudaStream_t st) {
   else if (va) wgrad_direct_kernel<8, 1><<<grid, 256, 0, st>>>(a);
   else if (vb) wgrad_direct_kernel<1, 8><<<grid, 256, 0, st>>>(a);
   else wgrad_direct_kernel<1, 1><<<grid, 256, 0, st>>>(a);
+  ++g_tem_launches;
   return cudaGetLastError();
 }
 
 cudaError_t launch_bias_grad(const void* P, int p_dtype, long long nvox, int C, float* db, cudaStream_t st) {
-  bias_grad_kernel<<<C, 256, 0, st>>>(P, p_dtype, nvox, C, db);
+  bias_grad_kernel<<<C, 256, 0, st>>>(P, p_dtype, nvox, C, db); ++g_tem_launches;
   return cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // Memory-bound helpers: fused loss kernels (cgan.py:110-142), multi-tensor Keras-Adam (cgan.py:69-73),
 // uint8 <-> standardised-float conventions (datasets.py:157-171,193-202; utils.py:109-125), stitching.
 #include "tem_kernels.cuh"
+extern unsigned long long g_tem_launches;
 #include <math.h>
 
 namespace {
@@ -214,48 +215,48 @@ inline unsigned grid_for(long long n, int threads = 256, long long cap = 148LL *
 
 cudaError_t launch_focal_logits(const float* x, long long n, float target, float gamma, float scale, int mode,
                                 float* loss_out, float* grad, cudaStream_t st) {
-  focal_logits_kernel<<<1, 256, 0, st>>>(x, n, target, gamma, scale, mode, loss_out, grad);
+  focal_logits_kernel<<<1, 256, 0, st>>>(x, n, target, gamma, scale, mode, loss_out, grad); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_pair_loss(const PairLossArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.N[0] * a.N[1] * a.N[2];
-  pair_loss_kernel<<<grid_for(total, 256, 148 * 4), 256, 0, st>>>(a);
+  pair_loss_kernel<<<grid_for(total, 256, 148 * 4), 256, 0, st>>>(a); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
                         float eps, float gscale, cudaStream_t st) {
-  adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+  adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_standardize_u8(const uint8_t* in, float* out, long long n, float mean, float stdv, cudaStream_t st) {
-  standardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv);
+  standardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_unstandardize_u8(const float* in, uint8_t* out, long long n, float mean, float stdv, cudaStream_t st) {
-  unstandardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv);
+  unstandardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_dropout_mask(uint32_t key, float* out, long long n, cudaStream_t st) {
-  dropout_mask_kernel<<<grid_for(n), 256, 0, st>>>(key, out, n);
+  dropout_mask_kernel<<<grid_for(n), 256, 0, st>>>(key, out, n); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t st) {
-  cast_bf16_f32_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n);
+  cast_bf16_f32_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st) {
-  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n);
+  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_init_normal(float* p, long long n, uint64_t seed, float stdv, cudaStream_t st) {
-  init_normal_kernel<<<grid_for(n), 256, 0, st>>>(p, n, seed, stdv);
+  init_normal_kernel<<<grid_for(n), 256, 0, st>>>(p, n, seed, stdv); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_stitch_u8(const StitchArgs& a, cudaStream_t st) {
-  stitch_u8_kernel<<<grid_for((long long)a.T * a.od * a.od * a.od), 256, 0, st>>>(a);
+  stitch_u8_kernel<<<grid_for((long long)a.T * a.od * a.od * a.od), 256, 0, st>>>(a); ++g_tem_launches;
   return cudaGetLastError();
 }
 cudaError_t launch_fetch_input_u8(const FetchInArgs& a, cudaStream_t st) {
-  fetch_input_u8_kernel<<<grid_for((long long)a.T * a.od * a.od * a.od), 256, 0, st>>>(a);
+  fetch_input_u8_kernel<<<grid_for((long long)a.T * a.od * a.od * a.od), 256, 0, st>>>(a); ++g_tem_launches;
   return cudaGetLastError();
 }

@@ -25,6 +25,50 @@ void tem_set_error(const char* fmt, ...) {
 extern "C" const char* tem_last_error(void) { return g_err; }
 extern "C" int tem_abi_version(void) { return TEM_ABI_VERSION; }
 
+unsigned long long g_tem_launches = 0;
+extern "C" uint64_t tem_launch_count(void) { return g_tem_launches; }
+
+static cudaEvent_t prof_event(Profiler& p) {
+  if (p.used == p.pool.size()) { cudaEvent_t e; cudaEventCreate(&e); p.pool.push_back(e); }
+  return p.pool[p.used++];
+}
+ProfScope::ProfScope(const tem_handle* hc, const char* layer, const char* op, double bytes, double flops, cudaStream_t s)
+    : h(const_cast<tem_handle*>(hc)), st(s), idx(0), live(false) {
+  if (!h || !h->prof.on) return;
+  ProfRec r; snprintf(r.tag, sizeof(r.tag), "%s.%s", layer, op);
+  r.e0 = prof_event(h->prof); r.e1 = prof_event(h->prof); r.bytes = bytes; r.flops = flops;
+  cudaEventRecord(r.e0, st);
+  idx = h->prof.recs.size(); h->prof.recs.push_back(r); live = true;
+}
+ProfScope::~ProfScope() { if (live) cudaEventRecord(h->prof.recs[idx].e1, st); }
+
+extern "C" int tem_profile_enable(tem_handle* h, int on) {
+  if (!h) { tem_set_error("null handle"); return TEM_ERR_ARG; }
+  h->prof.on = on != 0; h->prof.recs.clear(); h->prof.used = 0;
+  return TEM_OK;
+}
+// text report, one line per tag: "tag count total_ms bytes_per_launch flops_per_launch"
+extern "C" int tem_profile_report(tem_handle* h, char* buf, int64_t buflen) {
+  if (!h || !buf || buflen < 1) { tem_set_error("bad arguments"); return TEM_ERR_ARG; }
+  cudaDeviceSynchronize();
+  struct Agg { std::string tag; long n; double ms, bytes, flops; };
+  std::vector<Agg> aggs;
+  for (auto& r : h->prof.recs) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg* a = nullptr;
+    for (auto& x : aggs) if (x.tag == r.tag) { a = &x; break; }
+    if (!a) { aggs.push_back({r.tag, 0, 0, 0, 0}); a = &aggs.back(); }
+    a->n++; a->ms += ms; a->bytes += r.bytes; a->flops += r.flops;
+  }
+  int64_t off = 0; buf[0] = 0;
+  for (auto& a : aggs) {
+    int w = snprintf(buf + off, (size_t)(buflen - off), "%s %ld %.6f %.1f %.1f\n", a.tag.c_str(), a.n, a.ms, a.bytes / a.n, a.flops / a.n);
+    if (w < 0 || off + w >= buflen) break;
+    off += w;
+  }
+  return TEM_OK;
+}
+
 #define ARG_FAIL(...) do { tem_set_error(__VA_ARGS__); return TEM_ERR_ARG; } while (0)
 
 // ------------------------------------------------------------------------------------------
@@ -147,7 +191,17 @@ static int run_forward(const tem_handle* h, const LayerSpec& L, const float* net
   set_out(a, out, 0, nullptr);
   a.Cout = L.cout; a.slope = L.slope; a.drop_key = L.dropout ? drop_key : 0;
   a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
-  TEM_CUDA(launch_conv_direct(a, st));
+  {
+    const double ovox = (double)B * out.d[0] * out.d[1] * out.d[2];
+    const double ivox = (double)B * ((double)s0.Z * s0.Y * s0.X);
+    const double esz_in = s0.dtype == DT_F32 ? 4 : (s0.dtype == DT_BF16 ? 2 : 1), esz_out = out.dtype == DT_F32 ? 4 : 2;
+    double bytes = ivox * C0 * esz_in + ovox * L.cout * esz_out + (double)L.w_count * 4;
+    if (s1) bytes += ovox * C1 * 2;     // cropped skip window
+    double taps = (double)a.k[0] * a.k[1] * a.k[2];
+    double macs = L.transposed ? ivox * L.cin * L.cout * taps : ovox * L.cin * L.cout * taps;
+    ProfScope ps(h, L.name, "fwd", bytes, 2 * macs, st);
+    TEM_CUDA(launch_conv_direct(a, st));
+  }
   return TEM_OK;
 }
 
@@ -177,7 +231,16 @@ static int run_dgrad(const tem_handle* h, const LayerSpec& L, const float* netp,
     a.ref_slope = ref_slope;
   }
   a.drop_key = drop_key; a.accumulate = accumulate;
-  TEM_CUDA(launch_conv_direct(a, st));
+  {
+    const double dvox = (double)B * dy.d[0] * dy.d[1] * dy.d[2];
+    const double xvox = (double)B * ext[0] * ext[1] * ext[2];
+    const double esz_out = out.dtype == DT_F32 ? 4 : 2;
+    double bytes = dvox * L.cout * (dy.dtype == DT_F32 ? 4 : 2) + xvox * ci_cnt * esz_out * (accumulate ? 2 : 1) + (ref ? xvox * ci_cnt * 2 : 0) + (double)L.w_count * 4;
+    double taps = (double)a.k[0] * a.k[1] * a.k[2];
+    double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
+    ProfScope ps(h, L.name, "dgrad", bytes, 2 * macs, st);
+    TEM_CUDA(launch_conv_direct(a, st));
+  }
   return TEM_OK;
 }
 
@@ -204,7 +267,16 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     a.ws_tap = (long long)L.cin * L.cout; a.ws_a = L.cin; a.ws_b = 1;
   }
   a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
-  TEM_CUDA(launch_wgrad_direct(a, st));
+  {
+    const double dvox = (double)B * dy.d[0] * dy.d[1] * dy.d[2];
+    const double xvox = (double)B * ((double)x.Z * x.Y * x.X);
+    const double esz_x = x.dtype == DT_F32 ? 4 : (x.dtype == DT_BF16 ? 2 : 1);
+    double bytes = dvox * L.cout * (dy.dtype == DT_F32 ? 4 : 2) + xvox * ci_cnt * esz_x + (double)L.w_count * 4;
+    double taps = (double)a.k[0] * a.k[1] * a.k[2];
+    double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
+    ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
+    TEM_CUDA(launch_wgrad_direct(a, st));
+  }
   return TEM_OK;
 }
 
@@ -754,7 +826,7 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
 
 static int write_losses(tem_handle* h, float scale, float* losses_out, cudaStream_t st) {
   if (!losses_out) return TEM_OK;
-  finalize_losses_kernel<<<1, 32, 0, st>>>(h->loss_dev, scale, h->loss_dev + 9);
+  finalize_losses_kernel<<<1, 32, 0, st>>>(h->loss_dev, scale, h->loss_dev + 9); ++g_tem_launches;
   TEM_CUDA(cudaGetLastError());
   TEM_CUDA(cudaMemcpyAsync(losses_out, h->loss_dev + 9, 7 * sizeof(float), cudaMemcpyDefault, st));
   return TEM_OK;

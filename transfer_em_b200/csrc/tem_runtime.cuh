@@ -53,6 +53,15 @@ struct DiscPass {
 
 struct NcclApi;
 
+// optional per-launch CUDA-event timing, aggregated by (layer, op) tag: used by bench.py for the roofline line
+struct ProfRec { char tag[24]; cudaEvent_t e0, e1; double bytes, flops; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+};
+
 struct tem_handle {
   tem_config cfg;
   NetSpec nets[4];
@@ -79,7 +88,15 @@ struct tem_handle {
   void* comm; int rank, world;
   std::vector<void*> allocs;
   int last_gen_net, last_disc_net;
+  Profiler prof;
 };
+
+struct ProfScope {
+  tem_handle* h; cudaStream_t st; size_t idx; bool live;
+  ProfScope(const tem_handle* hc, const char* layer, const char* op, double bytes, double flops, cudaStream_t s);
+  ~ProfScope();
+};
+extern unsigned long long g_tem_launches;
 
 void tem_set_error(const char* fmt, ...);
 #define TEM_CUDA(expr)                                                                     \

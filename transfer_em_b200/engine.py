@@ -241,6 +241,23 @@ class Engine:
                                            C.c_void_p(inb.data_ptr()) if inb is not None else None, _stream()))
         return (inb, out) if fetch_input else out
 
+    # ---- measurement -----------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.tem_launch_count())
+
+    def profile(self, on):
+        check(self._lib.tem_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self):
+        """{tag: dict(count, ms, bytes, flops)} - per-launch algorithmic bytes / flops, total ms."""
+        buf = C.create_string_buffer(1 << 16)
+        check(self._lib.tem_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            t, n, ms, by, fl = line.split()
+            out[t] = dict(count=int(n), ms=float(ms), bytes=float(by), flops=float(fl))
+        return out
+
     # ---- data parallel ----------------------------------------------------------------------
     def init_comm(self, rank, world, broadcast_id):
         """broadcast_id(bytes_or_None) -> bytes: ships rank 0's 128-byte NCCL id to every rank."""
