@@ -182,3 +182,50 @@ def test_uint8_conventions_bit_exact():
         assert q.dtype == np.uint8 and np.array_equal(q, O.to_uint8_reference(y, ms))
         back = D.unstandardize_to_uint8(ref, ms)
         assert np.array_equal(back[..., 0], u)           # round trip uint8 -> float -> uint8 is the identity
+
+
+TC_CASES = [
+    # cin, cout, dims(z,y,x): tcgen05 implicit-GEMM path (3x3x3, stride 1)
+    (8, 8, (9, 20, 19)),        # Cin == 8: tap-pair k-steps, N padded 8 -> 16
+    (16, 16, (7, 18, 13)),
+    (32, 32, (8, 21, 12)),      # NPAD = 32
+    (8, 16, (12, 9, 10)),
+    (32, 16, (5, 35, 27)),      # several y / x tiles with ragged edges
+    (16, 32, (23, 10, 10)),     # z chunks
+]
+
+
+@pytest.mark.parametrize("cin,cout,dims", TC_CASES)
+def test_tcgen05_conv_fwd_dgrad(cin, cout, dims):
+    """tcgen05/TMA implicit GEMM vs the naive fp64 oracle on identical bf16 operands, and vs the direct kernel."""
+    r = np.random.default_rng(cin * 1000 + cout)
+    B = 2
+    x = bf16r(r.standard_normal((B,) + dims + (cin,)))
+    w = bf16r(r.standard_normal((3, 3, 3, cin, cout)) * 0.2)
+    xg, wg = _cuda(x, torch.bfloat16), _cuda(w, torch.float32)
+    d_tc = make_desc(B, dims, cin, cout, 3, 1, False, 0.3, 0, tc=1)
+    d_dir = make_desc(B, dims, cin, cout, 3, 1, False, 0.3, 0, tc=0)
+    y = conv_forward(xg, wg, d_tc).float().cpu().numpy()
+    ref = naive.lrelu(naive.conv_fwd(x, w, 1), 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    y_dir = conv_forward(xg, wg, d_dir).float().cpu().numpy()
+    assert rel_l2(y, y_dir) < 2e-3
+    dy = bf16r(r.standard_normal(ref.shape))
+    act = bf16r(r.standard_normal(x.shape))
+    dyg, actg = _cuda(dy, torch.bfloat16), _cuda(act, torch.bfloat16)
+    dx = conv_dgrad(dyg, wg, d_tc, actg, 0.3).float().cpu().numpy()
+    dref = naive.conv_dgrad(dy, w, 1, x.shape) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
+    assert rel_l2(dx, dref) < 4e-3
+
+
+def test_tcgen05_dropout_epilogue():
+    key = 0xABCDEF01
+    r = np.random.default_rng(77)
+    x = bf16r(r.standard_normal((1, 6, 18, 9, 16)))
+    w = bf16r(r.standard_normal((3, 3, 3, 16, 8)) * 0.2)
+    d = make_desc(1, (6, 18, 9), 16, 8, 3, 1, False, 0.3, key, tc=1)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w, torch.float32), d).float().cpu().numpy()
+    pre = naive.conv_fwd(x, w, 1)
+    ref = naive.lrelu(pre * O.dropout_keep_mask(key, pre.shape) * 2.0, 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)

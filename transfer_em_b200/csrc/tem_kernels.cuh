@@ -101,6 +101,12 @@ cudaError_t launch_conv_direct(const ConvArgs& a, cudaStream_t st);
 cudaError_t launch_wgrad_direct(const WgradArgs& a, cudaStream_t st);
 cudaError_t launch_bias_grad(const void* P, int p_dtype, long long nvox, int C, float* db, cudaStream_t st);
 
+// conv_tc.cu: tcgen05 implicit-GEMM path for 3x3x3 stride-1 convolutions (forward and data gradient)
+bool tc_conv_supported(const ConvArgs& a);
+size_t tc_packed_bytes(int cin, int cout);
+cudaError_t tc_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
+cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
+
 // elementwise.cu
 cudaError_t launch_focal_logits(const float* x, long long n, float target, float gamma, float scale, int mode,
                                 float* loss_out, float* grad, cudaStream_t st);

@@ -177,6 +177,38 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
   for (int i = 0; i < 3; ++i) a.out_off[i] = off ? off[i] : 0;
 }
 
+// conv dispatch: tcgen05 implicit GEMM when the shape allows, direct kernel otherwise
+static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
+  tem_handle* h = const_cast<tem_handle*>(hc);
+  for (int ax = 0; ax < 3; ++ax) if (a.L[ax] <= 0) return TEM_OK;
+  if (h->cfg.use_tensor_cores && tc_conv_supported(a)) {
+    const size_t bytes = tc_packed_bytes(a.C0 + a.C1, a.Cout);
+    if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
+      bf16* tmp = nullptr;
+      TEM_CUDA(cudaMallocAsync((void**)&tmp, bytes, st));
+      TEM_CUDA(tc_pack_weights(a, tmp, st));
+      TEM_CUDA(launch_conv_tc(a, tmp, st));
+      TEM_CUDA(cudaFreeAsync(tmp, st));
+      return TEM_OK;
+    }
+    auto key = std::make_tuple(a.w, a.form, a.Cout);
+    auto it = h->packed.find(key);
+    if (it == h->packed.end()) {
+      tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr;
+      TEM_CHECK(dev_alloc(h, (void**)&p.buf, bytes));
+      it = h->packed.emplace(key, p).first;
+    }
+    if (it->second.version != h->params_version) {
+      TEM_CUDA(tc_pack_weights(a, it->second.buf, st));
+      it->second.version = h->params_version;
+    }
+    TEM_CUDA(launch_conv_tc(a, it->second.buf, st));
+    return TEM_OK;
+  }
+  TEM_CUDA(launch_conv_direct(a, st));
+  return TEM_OK;
+}
+
 // forward of one layer: out = act(dropout(conv(cat(s0,s1)) + bias))
 static int run_forward(const tem_handle* h, const LayerSpec& L, const float* netp, const SrcView& s0, int C0,
                        const SrcView* s1, int C1, const Tensor& out, int B, uint32_t drop_key,
@@ -200,7 +232,7 @@ static int run_forward(const tem_handle* h, const LayerSpec& L, const float* net
     double taps = (double)a.k[0] * a.k[1] * a.k[2];
     double macs = L.transposed ? ivox * L.cin * L.cout * taps : ovox * L.cin * L.cout * taps;
     ProfScope ps(h, L.name, "fwd", bytes, 2 * macs, st);
-    TEM_CUDA(launch_conv_direct(a, st));
+    TEM_CHECK(dispatch_conv(h, a, st));
   }
   return TEM_OK;
 }
@@ -239,7 +271,7 @@ static int run_dgrad(const tem_handle* h, const LayerSpec& L, const float* netp,
     double taps = (double)a.k[0] * a.k[1] * a.k[2];
     double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
     ProfScope ps(h, L.name, "dgrad", bytes, 2 * macs, st);
-    TEM_CUDA(launch_conv_direct(a, st));
+    TEM_CHECK(dispatch_conv(h, a, st));
   }
   return TEM_OK;
 }
@@ -480,6 +512,7 @@ extern "C" int tem_comm_sync_params(tem_handle* h, void* stream) {
   TEM_NCCL(g_nccl.Broadcast(h->params, h->params, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
   TEM_NCCL(g_nccl.Broadcast(h->adam_m, h->adam_m, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
   TEM_NCCL(g_nccl.Broadcast(h->adam_v, h->adam_v, (size_t)h->total_params, kNcclFloat32, 0, h->comm, st));
+  h->params_version++;
   return TEM_OK;
 }
 
@@ -525,7 +558,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   TEM_CUDA(cudaSetDevice(cfg->device));
   tem_handle* h = new tem_handle();
   h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
-  h->keys_overridden = false; h->last_gen_net = 0; h->last_disc_net = 2;
+  h->keys_overridden = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
   h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
   h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
   long long off = 0;
@@ -643,6 +676,7 @@ extern "C" int tem_set_vector(tem_handle* h, int net, int which, const float* sr
   float* base = vec_ptr(h, which); if (!base) ARG_FAIL("bad vector selector %d", which);
   TEM_CUDA(cudaMemcpyAsync(base + h->nets[net].arena_off, src, (size_t)h->nets[net].count * 4, cudaMemcpyDefault, (cudaStream_t)stream));
   TEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (which == 0) h->params_version++;
   return TEM_OK;
 }
 extern "C" int tem_get_step(const tem_handle* h, int64_t* step) { if (!h || !step) ARG_FAIL("null"); *step = h->step; return TEM_OK; }
@@ -838,6 +872,7 @@ static int apply_adam(tem_handle* h, float gscale, cudaStream_t st) {
   const float lr_t = (float)(h->cfg.lr * sqrt(1.0 - pow(b2, (double)h->step)) / (1.0 - pow(b1, (double)h->step)));
   TEM_CUDA(launch_adam(h->params, h->grads, h->adam_m, h->adam_v, h->total_params, lr_t, h->cfg.beta1, h->cfg.beta2,
                        h->cfg.eps, gscale, st));
+  h->params_version++;
   return TEM_OK;
 }
 
@@ -1014,6 +1049,7 @@ static int desc_layer(const tem_conv_desc* d, tem_handle& fake, LayerSpec& L, in
   memset(&fake, 0, sizeof(tem_config));   // only nd is used by the helpers
   const bool is3 = !(d->in_dims[0] == 1 && d->k[0] == 1);
   fake.nd = is3 ? 3 : 2;
+  fake.cfg.use_tensor_cores = d->use_tensor_cores;
   if (d->k[1] != d->k[2] || (is3 && d->k[0] != d->k[1])) ARG_FAIL("kernel must be isotropic");
   if (d->stride[1] != d->stride[2]) ARG_FAIL("stride must be isotropic");
   L = mk("op", d->transposed, d->k[1], d->stride[1], d->cin, d->cout, d->slope, d->dropout_key != 0, 0);

@@ -1,6 +1,8 @@
 // Host-side runtime structures of libtem_b200: network tables, workspaces, pass executors.
 #pragma once
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "../../include/transfer_em_b200.h"
 #include "tem_kernels.cuh"
@@ -89,6 +91,10 @@ struct tem_handle {
   std::vector<void*> allocs;
   int last_gen_net, last_disc_net;
   Profiler prof;
+  // packed bf16 UMMA weight images, keyed by (weight pointer, form, columns); re-packed when params change
+  struct Packed { bf16* buf; size_t bytes; uint64_t version; };
+  std::map<std::tuple<const float*, int, int>, Packed> packed;
+  uint64_t params_version;
 };
 
 struct ProfScope {
