@@ -269,6 +269,9 @@ def main():
                      "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9, "hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm,
                      "achieved_tflops": step_flops / (ms_step * 1e-3) / 1e12, "bf16_frac_sustained": step_flops / (ms_step * 1e-3) / 1e12 / tf_sus,
                      "conv_kernel_ms_per_step": tot_ms / PK}
+    if os.environ.get("TEM_BENCH_TAGS"):
+        for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write("TAG %-12s n/step %5.1f ms/step %8.4f us/launch %9.2f GB/s %8.1f TFLOP/s %7.2f\n" % (k, v["count"] / PK, v["ms"] / PK, v["ms"] / v["count"] * 1e3, v["bytes"] * v["count"] / (v["ms"] * 1e-3) / 1e9, v["flops"] * v["count"] / (v["ms"] * 1e-3) / 1e12))
     top5 = sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:8]
     kernels = [{"tag": k, "ms_per_step": v["ms"] / PK, "gbs": v["bytes"] * v["count"] / (v["ms"] * 1e-3) / 1e9,
                 "tflops": v["flops"] * v["count"] / (v["ms"] * 1e-3) / 1e12} for k, v in top5]

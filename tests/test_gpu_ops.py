@@ -229,3 +229,38 @@ def test_tcgen05_dropout_epilogue():
     pre = naive.conv_fwd(x, w, 1)
     ref = naive.lrelu(pre * O.dropout_keep_mask(key, pre.shape) * 2.0, 0.3)
     np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
+WG_CASES = [
+    # k, s, cin, cout, transposed, dims
+    (3, 1, 8, 8, False, (9, 10, 21)),
+    (3, 1, 16, 16, False, (7, 8, 13)),
+    (3, 1, 32, 16, False, (6, 7, 19)),
+    (3, 1, 16, 32, False, (5, 9, 35)),
+    (4, 2, 8, 8, False, (10, 12, 38)),
+    (4, 2, 16, 16, False, (8, 10, 14)),
+    (4, 2, 32, 32, False, (6, 6, 8)),
+    (4, 2, 32, 16, True, (5, 6, 7)),
+    (4, 2, 16, 8, True, (6, 5, 20)),
+    (1, 1, 32, 32, False, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("k,s,cin,cout,tr,dims", WG_CASES)
+def test_tensor_core_wgrad(k, s, cin, cout, tr, dims):
+    """mma.sync weight gradient vs the naive fp64 oracle and vs the direct kernel."""
+    r = np.random.default_rng(k * 100 + cin + cout)
+    B = 2
+    x = bf16r(r.standard_normal((B,) + dims + (cin,)))
+    wshape = (k, k, k) + ((cout, cin) if tr else (cin, cout))
+    d_tc = make_desc(B, dims, cin, cout, k, s, tr, 1.0, 0, tc=1)
+    d_dir = make_desc(B, dims, cin, cout, k, s, tr, 1.0, 0, tc=0)
+    w0 = np.zeros(wshape)
+    yshape = (naive.convT_fwd(x, w0) if tr else naive.conv_fwd(x, w0, s)).shape
+    dy = bf16r(r.standard_normal(yshape))
+    xg, dyg = _cuda(x, torch.bfloat16), _cuda(dy, torch.bfloat16)
+    dw = conv_wgrad(xg, dyg, d_tc, wshape).cpu().numpy()
+    wref = naive.convT_wgrad(x, dy, (k, k, k)) if tr else naive.conv_wgrad(x, dy, s, (k, k, k))
+    assert rel_l2(dw, wref) < 1e-5
+    np.testing.assert_allclose(dw, wref, rtol=1e-4, atol=2e-3)
+    assert rel_l2(conv_wgrad(xg, dyg, d_dir, wshape).cpu().numpy(), dw) < 1e-5

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) conv_direct_kernel(const ConvArgs a)
       int co = i % CO_T; int r = i / CO_T; int ci = r % nci; int tap = r / nci;
       float wv = 0.f;
       if (co0 + co < a.Cout) wv = a.w[tap * a.ws_tap + (long long)(cc + ci) * a.ws_in + (long long)(co0 + co) * a.ws_out];
-      wsm[i] = wv;
+      wsm[i] = bf2f(__float2bfloat16_rn(wv));   // every conv kernel multiplies with the bf16 weight shadow
     }
     __syncthreads();
 

@@ -177,7 +177,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
               const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3)) * 16u;
               const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3)) * 16u;
-              const uint32_t lbo = (t1 == t0) ? 16u : (o1 - o0);
+              const uint32_t lbo = (t1 == t0) ? 0u : (o1 - o0);   // dummy half re-reads tap 8 (finite data x zero weights)
               umma_bf16(d_tmem, umma_desc(sbase + o0, lbo, HX * 16), umma_desc(wbase + (uint32_t)step * (NPAD * 32), NPAD * 16, 128), idesc, acc);
               acc = 1; ++step;
             }

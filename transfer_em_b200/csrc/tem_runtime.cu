@@ -307,7 +307,8 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     double taps = (double)a.k[0] * a.k[1] * a.k[2];
     double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
     ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
-    TEM_CUDA(launch_wgrad_direct(a, st));
+    if (h->cfg.use_tensor_cores && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
+    else TEM_CUDA(launch_wgrad_direct(a, st));
   }
   return TEM_OK;
 }

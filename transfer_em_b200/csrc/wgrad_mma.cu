@@ -1,0 +1,213 @@
+// Tensor-core weight gradient for the channel-narrow layers of the reference graph (Ca, Cb in {8,16,32,...}):
+//   dw[tap][ca][cb] += sum_{b,p} S[b, s*p + tap - pad][ca] * P[b,p][cb]          
+// (conv: S = layer input, P = dy; transposed conv: S = dy, P = layer input - models/utils.py:73,80,129-130).
+//
+// Why warp-level mma.sync (m16n8k16, bf16 -> fp32) and not tcgen05 here: the GEMM is M = (tap, ca) x N = cb x
+// K = voxels with ca, cb as small as 8.  tcgen05.mma needs M >= 64 with ONE uniform stride between its 8-row groups,
+// but the 8-channel groups of this M dimension are the taps, whose shared-memory offsets (dz*HY*HX + dy*HX + dx) are
+// not uniformly strided; padding M to 64 per tap costs 8x the tensor work.  m16n8k16 fits (2 taps x 8 ca) x 8 cb
+// exactly, and both operands come straight out of the natural [voxel][8 channels] layout with ldmatrix.trans.
+//
+// One CTA stages a (TZ x TY x 16) tile of output positions plus its input halo with cp.async (double buffered,
+// 8-channel planes so every ldmatrix row is a 16 B contiguous chunk), each warp owns up to 16 (M-tile, N-block)
+// accumulator tiles in registers, and partial sums leave through fp32 atomics once per CTA.
+#include <string.h>
+#include "tem_kernels.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kTPW = 16;          // accumulator tiles per warp
+constexpr int TXW = 16;           // x positions per K-step
+
+struct WgArgs {
+  const bf16* S; int SZ, SY, SX; int shift[3]; long long s_bstride;
+  const bf16* P; int PZ, PY, PX; int p_off[3]; long long p_bstride;
+  int Ca, Cb, B, L[3], k[3], stride[3], pad[3];
+  float* dw; long long ws_tap, ws_a, ws_b;
+  int TZ, TY;                       // tile (TZ x TY x 16 positions)
+  int HZ, HY, HX;                   // halo extents
+  int ntz, nty, ntx; long long ntiles; long long tiles_per_cta;
+  int Mtiles, NB, ntap, ntiles_out; // output tiling
+  int s_bytes, p_bytes;             // per-buffer shared memory sizes
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint32_t sbuf, uint32_t pbuf, int tid, int nthreads) {
+  long long t = tile;
+  const int tx = (int)(t % a.ntx); t /= a.ntx;
+  const int ty = (int)(t % a.nty); t /= a.nty;
+  const int tz = (int)(t % a.ntz); t /= a.ntz;
+  const int b = (int)t;
+  const int px0 = tx * TXW, py0 = ty * a.TY, pz0 = tz * a.TZ;
+  // S halo: voxel (hz,hy,hx) <-> S coordinate s*p0 - pad + h + shift
+  const int hvox = a.HZ * a.HY * a.HX;
+  const int pa = a.Ca >> 3;
+  const int sz0 = pz0 * a.stride[0] - a.pad[0] + a.shift[0], sy0 = py0 * a.stride[1] - a.pad[1] + a.shift[1], sx0 = px0 * a.stride[2] - a.pad[2] + a.shift[2];
+  const bf16* Sb = a.S + (long long)b * a.s_bstride;
+  for (int i = tid; i < hvox * pa; i += nthreads) {
+    const int plane = i % pa; const int v = i / pa;
+    const int hx = v % a.HX; const int r = v / a.HX; const int hy = r % a.HY; const int hz = r / a.HY;
+    const int z = sz0 + hz, y = sy0 + hy, x = sx0 + hx;
+    const bool ok = z >= 0 && z < a.SZ && y >= 0 && y < a.SY && x >= 0 && x < a.SX;
+    const bf16* src = ok ? Sb + (((long long)z * a.SY + y) * a.SX + x) * a.Ca + plane * 8 : a.S;
+    cp_async16(sbuf + (uint32_t)(plane * hvox + v) * 16u, src, ok);
+  }
+  // P tile: position (pz,py,px) <-> P coordinate p + p_off, zero outside the logical extent
+  const int tvox = a.TZ * a.TY * TXW;
+  const int pb = a.Cb >> 3;
+  const bf16* Pb = a.P + (long long)b * a.p_bstride;
+  for (int i = tid; i < tvox * pb; i += nthreads) {
+    const int plane = i % pb; const int v = i / pb;
+    const int px = v % TXW; const int r = v / TXW; const int py = r % a.TY; const int pz = r / a.TY;
+    const int z = pz0 + pz, y = py0 + py, x = px0 + px;
+    const bool ok = z < a.L[0] && y < a.L[1] && x < a.L[2];
+    const bf16* src = ok ? Pb + (((long long)(z + a.p_off[0]) * a.PY + y + a.p_off[1]) * a.PX + x + a.p_off[2]) * a.Cb + plane * 8 : a.P;
+    cp_async16(pbuf + (uint32_t)(plane * tvox + v) * 16u, src, ok);
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t buf_bytes = (uint32_t)(a.s_bytes + a.p_bytes);
+  const int hvox = a.HZ * a.HY * a.HX, tvox = a.TZ * a.TY * TXW;
+
+  // this warp's output tiles: tile id = nblk * Mtiles + mtile (consecutive ids share the P fragment)
+  const int tile0 = (blockIdx.y * kWarps + warp) * kTPW;
+  const int mat = lane >> 3, r8 = lane & 7;
+  const int a_half = mat & 1, a_vg = mat >> 1;        // A: matrices (v0-7,h0) (v0-7,h1) (v8-15,h0) (v8-15,h1)
+  const int b_v = ((lane >> 3) & 1) * 8 + r8;         // B: matrices (v0-7) (v8-15)
+  int aoff[kTPW], nblk[kTPW];                         // this thread's ldmatrix row offset (in 16 B voxels) per tile
+#pragma unroll
+  for (int i = 0; i < kTPW; ++i) {
+    const int id = tile0 + i;
+    const int idc = (id < a.ntiles_out) ? id : 0;
+    nblk[i] = idc / a.Mtiles;
+    const int m = idc % a.Mtiles;
+    int tap, plane;
+    if (a.Ca == 8) { tap = 2 * m + a_half; if (tap >= a.ntap) tap = 2 * m; plane = 0; }
+    else { const int cb16 = a.Ca >> 4; tap = m / cb16; plane = 2 * (m % cb16) + a_half; }
+    const int dx = tap % a.k[2], dy = (tap / a.k[2]) % a.k[1], dz = tap / (a.k[2] * a.k[1]);
+    aoff[i] = plane * hvox + (dz * a.HY + dy) * a.HX + dx + a.stride[2] * (a_vg * 8 + r8);
+  }
+  float acc[kTPW][4];
+#pragma unroll
+  for (int i = 0; i < kTPW; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+  const long long t_begin = (long long)blockIdx.x * a.tiles_per_cta;
+  const long long t_end = min(t_begin + a.tiles_per_cta, a.ntiles);
+  if (t_begin < t_end) stage_tile(a, t_begin, base, base + a.s_bytes, tid, kWarps * 32);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  for (long long t = t_begin; t < t_end; ++t) {
+    const int cur = (int)((t - t_begin) & 1);
+    if (t + 1 < t_end) stage_tile(a, t + 1, base + (cur ^ 1) * buf_bytes, base + (cur ^ 1) * buf_bytes + a.s_bytes, tid, kWarps * 32);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const uint32_t sbuf = base + cur * buf_bytes, pbuf = sbuf + a.s_bytes;
+    for (int row = 0; row < a.TZ * a.TY; ++row) {
+      const int pz = row / a.TY, py = row % a.TY;
+      const int rowbase = (pz * a.stride[0] * a.HY + py * a.stride[1]) * a.HX;
+      uint32_t b0 = 0, b1 = 0; int bcur = -1;
+#pragma unroll
+      for (int i = 0; i < kTPW; ++i) {
+        if (tile0 + i >= a.ntiles_out) continue;        // warp-uniform
+        if (nblk[i] != bcur) {
+          bcur = nblk[i];
+          ldsm_x2_t(pbuf + (uint32_t)(bcur * tvox + row * TXW + b_v) * 16u, b0, b1);
+        }
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4_t(sbuf + (uint32_t)(rowbase + aoff[i]) * 16u, a0, a1, a2, a3);
+        mma_bf16(acc[i], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+  // D fragment: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = (row g+8, cols 2t,2t+1); row = (half, ca), col = cb
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int i = 0; i < kTPW; ++i) {
+    const int id = tile0 + i;
+    if (id >= a.ntiles_out) continue;
+    const int m = id % a.Mtiles;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      int tap, ca;
+      if (a.Ca == 8) { tap = 2 * m + hh; ca = g; if (tap >= a.ntap) continue; }
+      else { const int cb16 = a.Ca >> 4; tap = m / cb16; ca = (2 * (m % cb16) + hh) * 8 + g; }
+      float* dst = a.dw + tap * a.ws_tap + (long long)ca * a.ws_a + (long long)(nblk[i] * 8 + 2 * tq) * a.ws_b;
+      const float v0 = acc[i][2 * hh], v1 = acc[i][2 * hh + 1];
+      if (v0 != 0.f) atomicAdd(dst, v0);
+      if (v1 != 0.f) atomicAdd(dst + a.ws_b, v1);
+    }
+  }
+}
+
+}  // namespace
+
+bool wgrad_mma_supported(const WgradArgs& w) {
+  if (w.S.dtype != DT_BF16 || w.p_dtype != DT_BF16) return false;
+  if (w.S.origins || w.use_lut) return false;
+  if (w.Ca % 8 || w.Cb % 8 || w.Ca < 8 || w.Cb < 8) return false;
+  if (!(w.Ca == 8 || w.Ca % 16 == 0)) return false;
+  if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
+  for (int i = 0; i < 3; ++i) if (w.stride[i] > 2) return false;
+  return true;
+}
+
+cudaError_t launch_wgrad_mma(const WgradArgs& w, cudaStream_t st) {
+  WgArgs a; memset(&a, 0, sizeof(a));
+  a.S = (const bf16*)w.S.p; a.SZ = w.S.Z; a.SY = w.S.Y; a.SX = w.S.X; a.s_bstride = w.S.bstride;
+  a.P = (const bf16*)w.P; a.PZ = w.PZ; a.PY = w.PY; a.PX = w.PX; a.p_bstride = w.p_bstride;
+  for (int i = 0; i < 3; ++i) { a.shift[i] = w.S.shift[i]; a.p_off[i] = w.p_off[i]; a.L[i] = w.L[i]; a.k[i] = w.k[i]; a.stride[i] = w.stride[i]; a.pad[i] = w.pad[i]; }
+  a.Ca = w.Ca; a.Cb = w.Cb; a.B = w.B; a.dw = w.dw; a.ws_tap = w.ws_tap; a.ws_a = w.ws_a; a.ws_b = w.ws_b;
+  a.ntap = w.k[0] * w.k[1] * w.k[2];
+  a.Mtiles = (w.Ca == 8) ? (a.ntap + 1) / 2 : a.ntap * (w.Ca / 16);
+  a.NB = w.Cb / 8;
+  a.ntiles_out = a.Mtiles * a.NB;
+  if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
+  // tile: shrink until two buffers fit in ~96 KB
+  int TZ = (w.L[0] >= 2) ? 2 : 1, TY = (w.L[1] >= 4) ? 4 : (w.L[1] >= 2 ? 2 : 1);
+  auto bytes = [&](int tz, int ty, int& hz, int& hy, int& hx, int& sb, int& pb) {
+    hz = (tz - 1) * w.stride[0] + w.k[0]; hy = (ty - 1) * w.stride[1] + w.k[1]; hx = (TXW - 1) * w.stride[2] + w.k[2];
+    sb = ((hz * hy * hx * w.Ca * 2) + 127) & ~127; pb = ((tz * ty * TXW * w.Cb * 2) + 127) & ~127;
+    return 2 * (sb + pb);
+  };
+  int hz, hy, hx, sb, pb;
+  while (bytes(TZ, TY, hz, hy, hx, sb, pb) > 96 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ = 1; else TY >>= 1; }
+  const int smem = bytes(TZ, TY, hz, hy, hx, sb, pb);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  a.TZ = TZ; a.TY = TY; a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.p_bytes = pb;
+  a.ntz = (w.L[0] + TZ - 1) / TZ; a.nty = (w.L[1] + TY - 1) / TY; a.ntx = (w.L[2] + TXW - 1) / TXW;
+  a.ntiles = (long long)w.B * a.ntz * a.nty * a.ntx;
+  const int gy = (a.ntiles_out + kWarps * kTPW - 1) / (kWarps * kTPW);
+  long long gx = (2 * 148 + gy - 1) / gy;
+  if (gx > a.ntiles) gx = a.ntiles;
+  a.tiles_per_cta = (a.ntiles + gx - 1) / gx;
+  gx = (a.ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  static bool attr = false;
+  if (!attr) { cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr = true; }
+  wgrad_mma_kernel<<<dim3((unsigned)gx, gy), kWarps * 32, smem, st>>>(a); ++g_tem_launches;
+  return cudaGetLastError();
+}
