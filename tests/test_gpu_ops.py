@@ -264,3 +264,27 @@ def test_tensor_core_wgrad(k, s, cin, cout, tr, dims):
     assert rel_l2(dw, wref) < 1e-5
     np.testing.assert_allclose(dw, wref, rtol=1e-4, atol=2e-3)
     assert rel_l2(conv_wgrad(xg, dyg, d_dir, wshape).cpu().numpy(), dw) < 1e-5
+
+
+def test_single_channel_wgrads_fast_path():
+    """g0-type (Cin = 1, uint8 / fp32 input) and g11-type (Cout = 1, fp32 dy) weight gradients, dedicated kernels."""
+    r = np.random.default_rng(123)
+    B, dims = 2, (9, 11, 37)
+    u = r.integers(0, 256, (B,) + dims + (1,), dtype=np.uint8)
+    ms = (0.05, 0.6)
+    xs = O.standardize_population(O.scale_tensor(u[..., 0]), ms).astype(np.float64)
+    dy = bf16r(r.standard_normal((B, 7, 9, 35, 8)))
+    for tc in (1, 0):
+        d = make_desc(B, dims, 1, 8, 3, 1, False, 1.0, 0, torch.uint8, torch.bfloat16, ms, tc=tc)
+        dw = conv_wgrad(torch.tensor(u).to(DEV), _cuda(dy, torch.bfloat16), d, (3, 3, 3, 1, 8)).cpu().numpy()
+        assert rel_l2(dw, naive.conv_wgrad(xs, dy, 1, (3, 3, 3))) < 1e-5
+    xf = r.standard_normal((B,) + dims + (1,)).astype(np.float32)
+    d = make_desc(B, dims, 1, 8, 3, 1, False, 1.0, 0, torch.float32, torch.bfloat16, tc=1)
+    dw = conv_wgrad(torch.tensor(xf).to(DEV), _cuda(dy, torch.bfloat16), d, (3, 3, 3, 1, 8)).cpu().numpy()
+    assert rel_l2(dw, naive.conv_wgrad(xf.astype(np.float64), dy, 1, (3, 3, 3))) < 1e-5
+    # Cout = 1
+    x = bf16r(r.standard_normal((B,) + dims + (16,)))
+    dy1 = r.standard_normal((B, 7, 9, 35, 1)).astype(np.float32)
+    d = make_desc(B, dims, 16, 1, 3, 1, False, 1.0, 0, torch.bfloat16, torch.float32, tc=1)
+    dw = conv_wgrad(_cuda(x, torch.bfloat16), torch.tensor(dy1).to(DEV), d, (3, 3, 3, 16, 1)).cpu().numpy()
+    assert rel_l2(dw, naive.conv_wgrad(x, dy1.astype(np.float64), 1, (3, 3, 3))) < 1e-5

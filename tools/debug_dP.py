@@ -20,7 +20,7 @@ model.engine.train_grads(rx, ry)
 # oracle: identity loss of pass same_y = G(real_y) only
 T = [torch.tensor(p, requires_grad=True) for p in P['g']]
 ga = {}
-same_y = O.generator_forward(T, torch.tensor(ry), 8, is3d, quant=O.bf16_round, graph_acts=ga)
+same_y = O.generator_forward(T, torch.tensor(ry), 8, is3d, quant=O.bf16_round, qweights=True, graph_acts=ga)
 loss = O.identity_loss(O.crop_cl(torch.tensor(ry), 17), same_y)
 loss.backward()
 layers = O.generator_layers(8)
@@ -34,4 +34,4 @@ for i in range(11):
     e2 = (err**2).sum(axis=(0, -1))
     tot = e2.sum()
     sl = (slice(2, -2),)*(3 if is3d else 2)
-    print(f'g{i}', 'rel %.3e' % rel_l2(got, ref), 'interior share of err^2: %.3f' % (e2[sl].sum()/max(tot,1e-300)), 'shape', ref.shape)
+    print(f'g{i}', 'rel %.3e' % rel_l2(got, ref), 'norms got %.3e ref %.3e' % (np.linalg.norm(got), np.linalg.norm(ref)), 'interior share of err^2: %.3f' % (e2[sl].sum()/max(tot,1e-300)), 'shape', ref.shape)

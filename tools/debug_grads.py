@@ -1,4 +1,4 @@
-import sys, numpy as np, torch
+import sys, os, numpy as np, torch
 sys.path.insert(0, '.')
 from oracle import tem_oracle as O
 from transfer_em_b200 import EM2EM
@@ -7,7 +7,7 @@ from tests.gpu_helpers import rel_l2
 NETS = {'g': NET_G, 'f': NET_F, 'dx': NET_DX, 'dy': NET_DY}
 is3d = '--3d' in sys.argv
 B = 1 if is3d else 2
-scale = 4.0
+scale = float(os.environ.get("SCALE", "2.0"))
 r = np.random.default_rng(21)
 P = {}
 for k in NETS:
@@ -19,7 +19,7 @@ shape = (B,) + (74,)*(3 if is3d else 2) + (1,)
 rx = r.standard_normal(shape).astype(np.float32); ry = (r.standard_normal(shape)*0.8+0.1).astype(np.float32)
 losses = model.engine.train_grads(rx, ry)
 ov = {'fake_y': model.engine.train_output('fake_y'), 'fake_x': model.engine.train_output('fake_x')} if '--ov' in sys.argv else None
-ref = O.train_step_grads(P, rx, ry, 8, is3d, dtype=torch.float32, keep_outputs=True, quant=O.bf16_round if '--q' in sys.argv else None, override_fakes=ov)
+ref = O.train_step_grads(P, rx, ry, 8, is3d, dtype=torch.float32, keep_outputs=True, quant=O.bf16_round if '--q' in sys.argv else None, qweights='--q' in sys.argv, override_fakes=ov)
 print('losses gpu', [float(v) for v in losses]); print('losses ref', ref.losses)
 for name in ("fake_y","cycled_x","fake_x","cycled_y","same_x","same_y"):
     print(name, rel_l2(model.engine.train_output(name), ref.outputs[name]))

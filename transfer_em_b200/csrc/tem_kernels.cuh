@@ -111,6 +111,10 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t 
 bool wgrad_mma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);
 
+// wgrad_c1.cu: weight gradient of the single-channel first / last layers
+bool wgrad_c1_supported(const WgradArgs& a);
+cudaError_t launch_wgrad_c1(const WgradArgs& a, cudaStream_t st);
+
 // elementwise.cu
 cudaError_t launch_focal_logits(const float* x, long long n, float target, float gamma, float scale, int mode,
                                 float* loss_out, float* grad, cudaStream_t st);

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -181,7 +182,8 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
 static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   tem_handle* h = const_cast<tem_handle*>(hc);
   for (int ax = 0; ax < 3; ++ax) if (a.L[ax] <= 0) return TEM_OK;
-  if (h->cfg.use_tensor_cores && tc_conv_supported(a)) {
+  static const bool no_tc = getenv("TEM_NO_CONV_TC") != nullptr;   // debug knob
+  if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) {
     const size_t bytes = tc_packed_bytes(a.C0 + a.C1, a.Cout);
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
@@ -307,7 +309,9 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     double taps = (double)a.k[0] * a.k[1] * a.k[2];
     double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
     ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
-    if (h->cfg.use_tensor_cores && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
+    static const bool no_mma = getenv("TEM_NO_WGRAD_MMA") != nullptr, no_c1 = getenv("TEM_NO_WGRAD_C1") != nullptr;   // debug knobs
+    if (h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
+    else if (h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) TEM_CUDA(launch_wgrad_c1(a, st));
     else TEM_CUDA(launch_wgrad_direct(a, st));
   }
   return TEM_OK;
@@ -850,12 +854,17 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, st));
   TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, st));       // disc_x wrt D_x   :212
   TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, st));
-  TEM_CHECK(gen_backward(h, F, gp[1], h->dOut[1], h->dOut[0], st));            // cycled_x -> F, and into fake_y
-  TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], st));            // cycled_y -> G, and into fake_x
-  TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, st));
-  TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, st));
-  TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, st));
-  TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, st));
+  {
+    // debug knob: TEM_DEBUG_GEN_BWD=k runs only the first k generator backward passes (scratch then holds pass k)
+    static const char* lim_s = getenv("TEM_DEBUG_GEN_BWD");
+    const int lim = lim_s ? atoi(lim_s) : 6;
+    if (lim > 0) TEM_CHECK(gen_backward(h, F, gp[1], h->dOut[1], h->dOut[0], st));            // cycled_x -> F, and into fake_y
+    if (lim > 1) TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], st));            // cycled_y -> G, and into fake_x
+    if (lim > 2) TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, st));
+    if (lim > 3) TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, st));
+    if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, st));
+    if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, st));
+  }
   return TEM_OK;
 }
 

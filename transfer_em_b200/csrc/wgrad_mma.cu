@@ -31,6 +31,7 @@ struct WgArgs {
   int HZ, HY, HX;                   // halo extents
   int ntz, nty, ntx; long long ntiles; long long tiles_per_cta;
   int Mtiles, NB, ntap, ntiles_out; // output tiling
+  int G, tpg, rsplit;               // tile groups, tiles per group, row splitters per group
   int s_bytes, p_bytes;             // per-buffer shared memory sizes
 };
 
@@ -91,7 +92,12 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
   const int hvox = a.HZ * a.HY * a.HX, tvox = a.TZ * a.TY * TXW;
 
   // this warp's output tiles: tile id = nblk * Mtiles + mtile (consecutive ids share the P fragment)
-  const int tile0 = (blockIdx.y * kWarps + warp) * kTPW;
+  // warp -> (tile group, row part): with few output tiles the 8 warps split the K rows of a tile instead
+  int group, rpart;
+  if (a.G >= kWarps) { group = blockIdx.y * kWarps + warp; rpart = 0; }
+  else { group = warp % a.G; rpart = warp / a.G; if (rpart >= a.rsplit) group = a.G; }
+  const int tile0 = group * a.tpg;
+  const int tile_end = (group < a.G) ? min(tile0 + a.tpg, a.ntiles_out) : 0;
   const int mat = lane >> 3, r8 = lane & 7;
   const int a_half = mat & 1, a_vg = mat >> 1;        // A: matrices (v0-7,h0) (v0-7,h1) (v8-15,h0) (v8-15,h1)
   const int b_v = ((lane >> 3) & 1) * 8 + r8;         // B: matrices (v0-7) (v8-15)
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
 #pragma unroll
   for (int i = 0; i < kTPW; ++i) {
     const int id = tile0 + i;
-    const int idc = (id < a.ntiles_out) ? id : 0;
+    const int idc = (id < tile_end) ? id : 0;
     nblk[i] = idc / a.Mtiles;
     const int m = idc % a.Mtiles;
     int tap, plane;
@@ -124,13 +130,13 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
     const uint32_t sbuf = base + cur * buf_bytes, pbuf = sbuf + a.s_bytes;
-    for (int row = 0; row < a.TZ * a.TY; ++row) {
+    for (int row = rpart; row < a.TZ * a.TY; row += a.rsplit) {
       const int pz = row / a.TY, py = row % a.TY;
       const int rowbase = (pz * a.stride[0] * a.HY + py * a.stride[1]) * a.HX;
       uint32_t b0 = 0, b1 = 0; int bcur = -1;
 #pragma unroll
       for (int i = 0; i < kTPW; ++i) {
-        if (tile0 + i >= a.ntiles_out) continue;        // warp-uniform
+        if (tile0 + i >= tile_end) continue;        // warp-uniform
         if (nblk[i] != bcur) {
           bcur = nblk[i];
           ldsm_x2_t(pbuf + (uint32_t)(bcur * tvox + row * TXW + b_v) * 16u, b0, b1);
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
 #pragma unroll
   for (int i = 0; i < kTPW; ++i) {
     const int id = tile0 + i;
-    if (id >= a.ntiles_out) continue;
+    if (id >= tile_end) continue;
     const int m = id % a.Mtiles;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -201,7 +207,10 @@ cudaError_t launch_wgrad_mma(const WgradArgs& w, cudaStream_t st) {
   a.TZ = TZ; a.TY = TY; a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.p_bytes = pb;
   a.ntz = (w.L[0] + TZ - 1) / TZ; a.nty = (w.L[1] + TY - 1) / TY; a.ntx = (w.L[2] + TXW - 1) / TXW;
   a.ntiles = (long long)w.B * a.ntz * a.nty * a.ntx;
-  const int gy = (a.ntiles_out + kWarps * kTPW - 1) / (kWarps * kTPW);
+  a.G = (a.ntiles_out + kTPW - 1) / kTPW;
+  a.tpg = (a.ntiles_out + a.G - 1) / a.G;
+  a.rsplit = (a.G >= kWarps) ? 1 : kWarps / a.G;
+  const int gy = (a.G + kWarps - 1) / kWarps;
   long long gx = (2 * 148 + gy - 1) / gy;
   if (gx > a.ntiles) gx = a.ntiles;
   a.tiles_per_cta = (a.ntiles + gx - 1) / gx;
