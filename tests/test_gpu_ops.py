@@ -288,3 +288,38 @@ def test_single_channel_wgrads_fast_path():
     d = make_desc(B, dims, 16, 1, 3, 1, False, 1.0, 0, torch.bfloat16, torch.float32, tc=1)
     dw = conv_wgrad(_cuda(x, torch.bfloat16), torch.tensor(dy1).to(DEV), d, (3, 3, 3, 16, 1)).cpu().numpy()
     assert rel_l2(dw, naive.conv_wgrad(x, dy1.astype(np.float64), 1, (3, 3, 3))) < 1e-5
+
+
+CM_CASES = [
+    # k, s, cin, cout, transposed, dims
+    (4, 2, 8, 8, False, (10, 12, 38)),      # g2
+    (4, 2, 16, 16, False, (8, 10, 14)),     # g4
+    (4, 2, 32, 32, False, (6, 6, 8)),       # d4
+    (4, 2, 32, 32, False, (4, 4, 4)),       # d6
+    (4, 2, 32, 16, True, (5, 6, 7)),        # g6
+    (4, 2, 16, 8, True, (6, 5, 20)),        # g9
+    (1, 1, 32, 32, False, (1, 1, 1)),       # d7
+    (3, 1, 16, 24, False, (5, 6, 17)),      # generic shape (NB = 3)
+]
+
+
+@pytest.mark.parametrize("k,s,cin,cout,tr,dims", CM_CASES)
+def test_mma_conv_fwd_dgrad(k, s, cin, cout, tr, dims):
+    """mma.sync conv kernel (stride-2 / transposed / 1x1 layers) vs the naive fp64 oracle, forward + data gradient."""
+    r = np.random.default_rng(k * 1000 + cin * 10 + cout + int(tr))
+    B = 2
+    x = bf16r(r.standard_normal((B,) + dims + (cin,)))
+    wshape = (k, k, k) + ((cout, cin) if tr else (cin, cout))
+    w = bf16r(r.standard_normal(wshape) * 0.2)
+    d = make_desc(B, dims, cin, cout, k, s, tr, 0.3, 0, tc=1)
+    xg, wg = _cuda(x, torch.bfloat16), _cuda(w, torch.float32)
+    y = conv_forward(xg, wg, d).float().cpu().numpy()
+    ref = naive.lrelu(naive.convT_fwd(x, w) if tr else naive.conv_fwd(x, w, s), 0.3)
+    assert y.shape == ref.shape
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    dy = bf16r(r.standard_normal(ref.shape))
+    act = bf16r(r.standard_normal(x.shape))
+    dx = conv_dgrad(_cuda(dy, torch.bfloat16), wg, d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
+    dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
+    assert rel_l2(dx, dref) < 4e-3

@@ -107,6 +107,10 @@ size_t tc_packed_bytes(int cin, int cout);
 cudaError_t tc_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 
+// conv_mma.cu: mma.sync convolution for stride-2 / transposed / 1x1 layers with channel counts that are multiples of 8
+bool conv_mma_supported(const ConvArgs& a);
+cudaError_t launch_conv_mma(const ConvArgs& a, cudaStream_t st);
+
 // wgrad_mma.cu: tensor-core (mma.sync) weight gradient for channel counts that are multiples of 8
 bool wgrad_mma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);
