@@ -323,3 +323,29 @@ def test_mma_conv_fwd_dgrad(k, s, cin, cout, tr, dims):
     dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
     assert rel_l2(dx, dref) < 4e-3
+
+
+def test_single_channel_conv_fast_paths():
+    """1 -> C forward (uint8 / fp32), its flipped form (dgrad of a Cout=1 layer) and C -> 1 forward."""
+    r = np.random.default_rng(321)
+    B, dims = 2, (9, 13, 37)
+    u = r.integers(0, 256, (B,) + dims + (1,), dtype=np.uint8)
+    ms = (0.05, 0.6)
+    xs = O.standardize_population(O.scale_tensor(u[..., 0]), ms).astype(np.float64)
+    w = bf16r(r.standard_normal((3, 3, 3, 1, 8)) * 0.3)
+    for tc in (1, 0):
+        d = make_desc(B, dims, 1, 8, 3, 1, False, 0.3, 0, torch.uint8, torch.bfloat16, ms, tc=tc)
+        y = conv_forward(torch.tensor(u).to(DEV), _cuda(w, torch.float32), d).float().cpu().numpy()
+        np.testing.assert_allclose(y, naive.lrelu(naive.conv_fwd(xs, w, 1), 0.3), rtol=BF16_RTOL, atol=BF16_ATOL)
+    # C -> 1 forward (fp32 out) and its data gradient (1 -> C, flipped, pad 2, LeakyReLU' of the stored activation)
+    x = bf16r(r.standard_normal((B,) + dims + (16,)))
+    w1 = bf16r(r.standard_normal((3, 3, 3, 16, 1)) * 0.2)
+    d = make_desc(B, dims, 16, 1, 3, 1, False, 1.0, 0, torch.bfloat16, torch.float32, tc=1)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w1, torch.float32), d).cpu().numpy()
+    ref = naive.conv_fwd(x, w1, 1)
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-4)
+    dy = r.standard_normal(ref.shape).astype(np.float32)
+    act = bf16r(r.standard_normal(x.shape))
+    dx = conv_dgrad(torch.tensor(dy).to(DEV), _cuda(w1, torch.float32), d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
+    dref = naive.conv_dgrad(dy.astype(np.float64), w1, 1, x.shape) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 2)

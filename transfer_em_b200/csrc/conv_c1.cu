@@ -1,0 +1,215 @@
+// Dedicated memory-bound kernels for the single-channel ends of the networks (no tensor cores: K = 27 or N = 1):
+//   conv_c1in_kernel<CO>:  1 -> CO channels, 3x3x3 stride 1 (g0 / d0 forward: generator.py:54, discriminator.py:39;
+//                          and, with flipped weights + zero padding, the data gradient of the Cout = 1 layer g11)
+//   conv_c1out_kernel<CI>: CI -> 1 channel, 3x3x3 stride 1 (g11 forward: generator.py:110), fp32 output
+// A CTA stages the input halo of a 4 x 8 x 32 output tile in shared memory once (uint8 goes through the standardise
+// LUT, fp32/bf16 fakes get their virtual zero padding, tiles may come from per-sample origins in one volume), every
+// thread then produces 4 z-consecutive voxels with a register sliding window: FMA-bound inner loop, 16 B coalesced
+// stores, fused LeakyReLU / LeakyReLU' * dropout epilogues.
+#include <string.h>
+#include "tem_kernels.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int TZ = 4, TY = 8, TXT = 32;
+constexpr int HZc = TZ + 2, HYc = TY + 2, HXc = TXT + 2;
+
+__device__ __forceinline__ float ld1(const SrcView& S, long long off, const float* lut) {
+  if (S.dtype == DT_U8) return lut[reinterpret_cast<const uint8_t*>(S.p)[off]];
+  if (S.dtype == DT_BF16) return bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
+  return reinterpret_cast<const float*>(S.p)[off];
+}
+
+template <int CO>
+__global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz, const int flip) {
+  __shared__ float lut[256];
+  __shared__ float tile[HZc * HYc * HXc];
+  __shared__ __align__(16) float wsm[27 * CO];
+  const int tid = threadIdx.x;
+  if (a.use_lut) for (int i = tid; i < 256; i += 256) lut[i] = tem_standardize((float)i, a.lut_mean, a.lut_std);
+  for (int i = tid; i < 27 * CO; i += 256) {
+    const int co = i % CO; int tap = i / CO;
+    if (flip) tap = 26 - tap;
+    wsm[i] = (co < a.Cout) ? bf2f(__float2bfloat16_rn(a.w[tap * a.ws_tap + (long long)co * a.ws_out])) : 0.f;
+  }
+  int t = blockIdx.x;
+  const int tx = t % ntx; t /= ntx;
+  const int ty = t % nty; t /= nty;
+  const int tz = t % ntz; t /= ntz;
+  const int b = t;
+  const int z0 = tz * TZ, y0 = ty * TY, x0 = tx * TXT;
+  __syncthreads();
+  // stage: logical conv-input coordinate of halo voxel (hz,hy,hx) = (z0,y0,x0) + h - pad ; tensor = logical + shift
+  const SrcView& S = a.s0;
+  const int pad = flip ? 2 : 0;
+  int oz = 0, oy = 0, ox = 0; long long sbase = (long long)b * S.bstride;
+  if (S.origins) { oz = S.origins[b * 3]; oy = S.origins[b * 3 + 1]; ox = S.origins[b * 3 + 2]; sbase = 0; }
+  const float fill = (a.use_lut && S.origins) ? lut[0] : 0.f;
+  for (int i = tid; i < HZc * HYc * HXc; i += 256) {
+    const int hx = i % HXc; const int r = i / HXc; const int hy = r % HYc; const int hz = r / HYc;
+    const int z = z0 + hz - pad + S.shift[0] + oz, y = y0 + hy - pad + S.shift[1] + oy, x = x0 + hx - pad + S.shift[2] + ox;
+    float v = fill;
+    if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
+      v = ld1(S, sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff, lut);
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int lx = tid & 31, ly = tid >> 5;        // 32 x 8 threads, 4 voxels in z each
+  float acc[TZ][CO];
+#pragma unroll
+  for (int j = 0; j < TZ; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      float col[HZc];
+#pragma unroll
+      for (int hz = 0; hz < HZc; ++hz) col[hz] = tile[(hz * HYc + ly + dy) * HXc + lx + dx];
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz) {
+        const float* wr = wsm + ((dz * 3 + dy) * 3 + dx) * CO;
+        float wv[CO];
+#pragma unroll
+        for (int c = 0; c < CO; c += 4) { const float4 w4 = *reinterpret_cast<const float4*>(wr + c); wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w; }
+#pragma unroll
+        for (int j = 0; j < TZ; ++j)
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(col[j + dz], wv[c], acc[j][c]);
+      }
+    }
+  const int oy_ = y0 + ly, ox_ = x0 + lx;
+  if (oy_ >= a.L[1] || ox_ >= a.L[2]) return;
+#pragma unroll
+  for (int j = 0; j < TZ; ++j) {
+    const int oz_ = z0 + j;
+    if (oz_ >= a.L[0]) break;
+    float v[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) v[c] = acc[j][c];
+    if (a.ref) {
+      const long long ro = ((((long long)b * a.RZ + oz_ + a.ref_off[0]) * a.RY + oy_ + a.ref_off[1]) * a.RX + ox_ + a.ref_off[2]) * a.ref_C + a.ref_coff;
+#pragma unroll
+      for (int c = 0; c < CO; c += 8) {
+        float f[8]; unpack8(*reinterpret_cast<const uint4*>(a.ref + ro + c), f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
+      }
+    }
+    if (a.drop_key) {
+      const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz_) * a.L[1] + oy_) * a.L[2] + ox_) * a.Cout);
+#pragma unroll
+      for (int c = 0; c < CO; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
+    }
+    bf16* op = reinterpret_cast<bf16*>(a.out) + ((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff;
+#pragma unroll
+    for (int c = 0; c < CO; c += 8) {
+      float o[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { o[u] = v[c + u]; if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope; }
+      uint4 pk; pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(op + c) = pk;
+    }
+  }
+}
+
+// CI -> 1 channel, fp32 output (linear), bf16 input staged as 8-channel planes of uint4
+template <int CI>
+__global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint4* tile = reinterpret_cast<uint4*>(smem_raw);                 // [CI/8][HZ][HY][HX]
+  __shared__ __align__(16) float wsm[27 * CI];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * CI; i += 256) wsm[i] = bf2f(__float2bfloat16_rn(a.w[(i / CI) * a.ws_tap + (long long)(i % CI) * a.ws_in]));
+  int t = blockIdx.x;
+  const int tx = t % ntx; t /= ntx;
+  const int ty = t % nty; t /= nty;
+  const int tz = t % ntz; t /= ntz;
+  const int b = t;
+  const int z0 = tz * TZ, y0 = ty * TY, x0 = tx * TXT;
+  const SrcView& S = a.s0;
+  constexpr int HV = HZc * HYc * HXc, PL = CI / 8;
+  const bf16* Sb = reinterpret_cast<const bf16*>(S.p) + (long long)b * S.bstride;
+  for (int i = tid; i < HV * PL; i += 256) {
+    const int pl = i % PL; const int v = i / PL;
+    const int hx = v % HXc; const int r = v / HXc; const int hy = r % HYc; const int hz = r / HYc;
+    const int z = z0 + hz + S.shift[0], y = y0 + hy + S.shift[1], x = x0 + hx + S.shift[2];
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
+      q = __ldg(reinterpret_cast<const uint4*>(Sb + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff + pl * 8));
+    tile[pl * HV + v] = q;
+  }
+  __syncthreads();
+  const int lx = tid & 31, ly = tid >> 5;
+  float acc[TZ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int pl = 0; pl < PL; ++pl)
+#pragma unroll
+        for (int hz = 0; hz < HZc; ++hz) {
+          float f[8]; unpack8(tile[pl * HV + (hz * HYc + ly + dy) * HXc + lx + dx], f);
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            const int j = hz - dz;
+            if (j < 0 || j >= TZ) continue;
+            const float* wr = wsm + ((dz * 3 + dy) * 3 + dx) * CI + pl * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+            acc[j] = fmaf(f[0], w0.x, fmaf(f[1], w0.y, fmaf(f[2], w0.z, fmaf(f[3], w0.w,
+                     fmaf(f[4], w1.x, fmaf(f[5], w1.y, fmaf(f[6], w1.z, fmaf(f[7], w1.w, acc[j]))))))));
+          }
+        }
+  const int oy_ = y0 + ly, ox_ = x0 + lx;
+  if (oy_ >= a.L[1] || ox_ >= a.L[2]) return;
+  float* out = reinterpret_cast<float*>(a.out);
+#pragma unroll
+  for (int j = 0; j < TZ; ++j) {
+    const int oz_ = z0 + j;
+    if (oz_ >= a.L[0]) break;
+    float v = acc[j];
+    if (a.slope != 1.f) v = v > 0.f ? v : v * a.slope;
+    out[((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff] = v;
+  }
+}
+
+}  // namespace
+
+bool conv_c1_supported(const ConvArgs& a) {
+  if (a.C1 != 0 || a.bias || a.accumulate) return false;
+  for (int i = 0; i < 3; ++i) if (a.k[i] != 3 || a.stride[i] != 1 || a.conv_off[i]) return false;
+  if (a.C0 == 1 && (a.Cout == 8 || a.Cout == 16) && a.out_dtype == DT_BF16 && a.out_C % 8 == 0 && a.out_coff % 8 == 0 &&
+      (!a.ref || (a.ref_C % 8 == 0 && a.ref_coff % 8 == 0)))
+    return true;                                                     // 1 -> C (form 0 forward, form 1 = flipped + pad 2)
+  if (a.form == 0 && a.Cout == 1 && a.out_dtype == DT_F32 && a.s0.dtype == DT_BF16 && (a.C0 == 8 || a.C0 == 16 || a.C0 == 32) &&
+      a.s0.C % 8 == 0 && a.s0.coff % 8 == 0 && !a.s0.origins && !a.ref && !a.drop_key)
+    return true;                                                     // C -> 1 forward
+  return false;
+}
+
+cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st) {
+  const int ntx = (a.L[2] + TXT - 1) / TXT, nty = (a.L[1] + TY - 1) / TY, ntz = (a.L[0] + TZ - 1) / TZ;
+  const long long grid = (long long)a.B * ntx * nty * ntz;
+  if (grid == 0) return cudaSuccess;
+  if (a.C0 == 1) {
+    if (a.Cout == 8) conv_c1in_kernel<8><<<(unsigned)grid, 256, 0, st>>>(a, ntx, nty, ntz, a.form == 1);
+    else conv_c1in_kernel<16><<<(unsigned)grid, 256, 0, st>>>(a, ntx, nty, ntz, a.form == 1);
+  } else {
+    const size_t smem = (size_t)HZc * HYc * HXc * (a.C0 / 8) * 16;
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(conv_c1out_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); if (e) return e;
+      e = cudaFuncSetAttribute(conv_c1out_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); if (e) return e;
+      attr = true;
+    }
+    if (a.C0 == 8) conv_c1out_kernel<8><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
+    else if (a.C0 == 16) conv_c1out_kernel<16><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
+    else conv_c1out_kernel<32><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
+  }
+  ++g_tem_launches;
+  return cudaGetLastError();
+}

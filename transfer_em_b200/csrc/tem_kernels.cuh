@@ -111,6 +111,10 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t 
 bool conv_mma_supported(const ConvArgs& a);
 cudaError_t launch_conv_mma(const ConvArgs& a, cudaStream_t st);
 
+// conv_c1.cu: dedicated kernels for the single-channel first / last layers (1 -> C and C -> 1, 3x3x3 stride 1)
+bool conv_c1_supported(const ConvArgs& a);
+cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st);
+
 // wgrad_mma.cu: tensor-core (mma.sync) weight gradient for channel counts that are multiples of 8
 bool wgrad_mma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);

@@ -207,6 +207,8 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
     TEM_CUDA(launch_conv_tc(a, it->second.buf, st));
     return TEM_OK;
   }
+  static const bool no_c1 = getenv("TEM_NO_CONV_C1") != nullptr;     // debug knob
+  if (h->cfg.use_tensor_cores && !no_c1 && conv_c1_supported(a)) { TEM_CUDA(launch_conv_c1(a, st)); return TEM_OK; }
   static const bool no_mma = getenv("TEM_NO_CONV_MMA") != nullptr;   // debug knob
   if (h->cfg.use_tensor_cores && !no_mma && conv_mma_supported(a)) { TEM_CUDA(launch_conv_mma(a, st)); return TEM_OK; }
   TEM_CUDA(launch_conv_direct(a, st));

@@ -15,109 +15,139 @@ __device__ __forceinline__ float load1(const SrcView& S, long long off, const fl
   return reinterpret_cast<const float*>(S.p)[off];
 }
 
-// Ca == 1.  blockIdx.y = kz tap plane, blockIdx.z = 8-channel block of P.  Each thread owns KY*KX x 8 accumulators
-// over its positions (lanes = consecutive positions -> coalesced P and S reads), then a shuffle reduction.
-template <int KYX>
-__global__ void __launch_bounds__(128) wgrad_cin1_kernel(const WgradArgs a) {
+constexpr int WZ = 4, WY = 8, WX = 32;                 // positions per tile; 256 threads = 32 x 8, 4 z-positions each
+constexpr int HZw = WZ + 2, HYw = WY + 2, HXw = WX + 2;
+
+__device__ __forceinline__ void decode_tile(long long t, int ntx, int nty, int ntz, int& b, int& z0, int& y0, int& x0) {
+  const int tx = (int)(t % ntx); t /= ntx;
+  const int ty = (int)(t % nty); t /= nty;
+  const int tz = (int)(t % ntz); t /= ntz;
+  b = (int)t; z0 = tz * WZ; y0 = ty * WY; x0 = tx * WX;
+}
+
+// Ca == 1 (3x3x3, stride 1).  blockIdx.y = kz tap plane, blockIdx.z = 8-channel block of P.  The S halo of a tile is
+// staged in shared memory as float; every thread keeps 9 x 8 accumulators over all the tiles of its CTA, then one
+// shuffle reduction + atomics.
+__global__ void __launch_bounds__(256) wgrad_cin1_kernel(const WgradArgs a, const int ntx, const int nty, const int ntz,
+                                                         const long long ntiles, const long long tiles_per_cta) {
   __shared__ float lut[256];
-  if (a.use_lut) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = tem_standardize((float)i, a.lut_mean, a.lut_std);
-    __syncthreads();
-  }
+  __shared__ float tile[HZw * HYw * HXw];
+  const int tid = threadIdx.x;
+  if (a.use_lut) for (int i = tid; i < 256; i += 256) lut[i] = tem_standardize((float)i, a.lut_mean, a.lut_std);
   const int dz = blockIdx.y, cb0 = blockIdx.z * 8;
-  const int kx = a.k[2];
-  float acc[KYX][8];
+  float acc[9][8];
 #pragma unroll
-  for (int t = 0; t < KYX; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
   const SrcView& S = a.S;
-  const long long v0 = (long long)blockIdx.x * a.vox_per_cta, v1 = min(v0 + a.vox_per_cta, a.nvox);
-  for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
-    long long t = v;
-    const int lx = (int)(t % a.L[2]); t /= a.L[2];
-    const int ly = (int)(t % a.L[1]); t /= a.L[1];
-    const int lz = (int)(t % a.L[0]); t /= a.L[0];
-    const int b = (int)t;
-    const long long po = (long long)b * a.p_bstride + ((((long long)lz + a.p_off[0]) * a.PY + ly + a.p_off[1]) * a.PX + lx + a.p_off[2]) * a.p_C + a.p_coff + cb0;
-    float pb[8];
-    if (a.p_dtype == DT_BF16) unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.P) + po)), pb);
-    else {
-      const float4* fp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.P) + po);
-      const float4 x0 = fp[0], x1 = fp[1];
-      pb[0] = x0.x; pb[1] = x0.y; pb[2] = x0.z; pb[3] = x0.w; pb[4] = x1.x; pb[5] = x1.y; pb[6] = x1.z; pb[7] = x1.w;
-    }
-    int tz = lz + dz - a.pad[0] + S.shift[0], ty0 = ly - a.pad[1] + S.shift[1], tx0 = lx - a.pad[2] + S.shift[2];
-    long long sbase;
-    if (S.origins) { tz += S.origins[b * 3]; ty0 += S.origins[b * 3 + 1]; tx0 += S.origins[b * 3 + 2]; sbase = 0; }
-    else sbase = (long long)b * S.bstride;
+  const int lx = tid & 31, ly = tid >> 5;
+  const long long t0 = (long long)blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
+  for (long long tl = t0; tl < t1; ++tl) {
+    int b, z0, y0, x0; decode_tile(tl, ntx, nty, ntz, b, z0, y0, x0);
+    int oz = 0, oy = 0, ox = 0; long long sbase = (long long)b * S.bstride;
+    if (S.origins) { oz = S.origins[b * 3]; oy = S.origins[b * 3 + 1]; ox = S.origins[b * 3 + 2]; sbase = 0; }
+    __syncthreads();
     const float fill = (a.use_lut && S.origins) ? lut[0] : 0.f;
-    const bool zin = tz >= 0 && tz < S.Z;
+    // only the z-planes dz .. dz+WZ-1 of the halo are needed by this CTA
+    for (int i = tid; i < WZ * HYw * HXw; i += 256) {
+      const int hx = i % HXw; const int r = i / HXw; const int hy = r % HYw; const int hz = r / HYw;
+      const int z = z0 + hz + dz - a.pad[0] + S.shift[0] + oz, y = y0 + hy - a.pad[1] + S.shift[1] + oy, x = x0 + hx - a.pad[2] + S.shift[2] + ox;
+      float v = fill;
+      if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X) v = load1(S, sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff, lut);
+      tile[i] = v;
+    }
+    __syncthreads();
+    const int py = y0 + ly, px = x0 + lx;
+    if (py < a.L[1] && px < a.L[2]) {
 #pragma unroll
-    for (int tp = 0; tp < KYX; ++tp) {
-      const int ty = ty0 + tp / kx, tx = tx0 + tp % kx;
-      float sv = fill;
-      if (zin && ty >= 0 && ty < S.Y && tx >= 0 && tx < S.X)
-        sv = load1(S, sbase + (((long long)tz * S.Y + ty) * S.X + tx) * S.C + S.coff, lut);
+      for (int j = 0; j < WZ; ++j) {
+        const int pz = z0 + j;
+        if (pz >= a.L[0]) break;
+        const long long po = (long long)b * a.p_bstride + ((((long long)pz + a.p_off[0]) * a.PY + py + a.p_off[1]) * a.PX + px + a.p_off[2]) * a.p_C + a.p_coff + cb0;
+        float pb[8];
+        if (a.p_dtype == DT_BF16) unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.P) + po)), pb);
+        else {
+          const float4* fp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.P) + po);
+          const float4 x0v = fp[0], x1v = fp[1];
+          pb[0] = x0v.x; pb[1] = x0v.y; pb[2] = x0v.z; pb[3] = x0v.w; pb[4] = x1v.x; pb[5] = x1v.y; pb[6] = x1v.z; pb[7] = x1v.w;
+        }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[tp][c] = fmaf(sv, pb[c], acc[tp][c]);
+        for (int tp = 0; tp < 9; ++tp) {
+          const float sv = tile[(j * HYw + ly + tp / 3) * HXw + lx + tp % 3];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[tp][c] = fmaf(sv, pb[c], acc[tp][c]);
+        }
+      }
     }
   }
-  const int lane = threadIdx.x & 31;
+  const int lane = tid & 31;
 #pragma unroll
-  for (int tp = 0; tp < KYX; ++tp)
+  for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      float s = acc[tp][c];
+      float sum = acc[tp][c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == ((tp * 8 + c) & 31) && cb0 + c < a.Cb && s != 0.f)
-        atomicAdd(a.dw + (long long)(dz * KYX + tp) * a.ws_tap + (long long)(cb0 + c) * a.ws_b, s);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == ((tp * 8 + c) & 31) && cb0 + c < a.Cb && sum != 0.f)
+        atomicAdd(a.dw + (long long)(dz * 9 + tp) * a.ws_tap + (long long)(cb0 + c) * a.ws_b, sum);
     }
 }
 
 // Cb == 1 (P fp32 or bf16, one channel).  blockIdx.y = (kz, ky) tap row, blockIdx.z = 8-channel block of S.
-template <int KX>
-__global__ void __launch_bounds__(128) wgrad_cout1_kernel(const WgradArgs a) {
-  const int dz = blockIdx.y / a.k[1], dy = blockIdx.y % a.k[1], ca0 = blockIdx.z * 8;
-  float acc[KX][8];
+__global__ void __launch_bounds__(256) wgrad_cout1_kernel(const WgradArgs a, const int ntx, const int nty, const int ntz,
+                                                          const long long ntiles, const long long tiles_per_cta) {
+  __shared__ uint4 tile[WZ * WY * HXw];          // the (dz,dy)-shifted rows of this CTA's 8-channel block
+  const int tid = threadIdx.x;
+  const int dz = blockIdx.y / 3, dy = blockIdx.y % 3, ca0 = blockIdx.z * 8;
+  float acc[3][8];
 #pragma unroll
-  for (int t = 0; t < KX; ++t)
+  for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
   const SrcView& S = a.S;
-  const long long v0 = (long long)blockIdx.x * a.vox_per_cta, v1 = min(v0 + a.vox_per_cta, a.nvox);
-  for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
-    long long t = v;
-    const int lx = (int)(t % a.L[2]); t /= a.L[2];
-    const int ly = (int)(t % a.L[1]); t /= a.L[1];
-    const int lz = (int)(t % a.L[0]); t /= a.L[0];
-    const int b = (int)t;
-    const long long po = (long long)b * a.p_bstride + ((((long long)lz + a.p_off[0]) * a.PY + ly + a.p_off[1]) * a.PX + lx + a.p_off[2]) * a.p_C + a.p_coff;
-    const float pv = (a.p_dtype == DT_BF16) ? bf2f(reinterpret_cast<const bf16*>(a.P)[po]) : reinterpret_cast<const float*>(a.P)[po];
-    const int tz = lz + dz - a.pad[0] + S.shift[0], ty = ly + dy - a.pad[1] + S.shift[1], tx0 = lx - a.pad[2] + S.shift[2];
-    if (tz < 0 || tz >= S.Z || ty < 0 || ty >= S.Y) continue;
-    const long long so = (long long)b * S.bstride + (((long long)tz * S.Y + ty) * S.X + tx0) * S.C + S.coff + ca0;
+  const int lx = tid & 31, ly = tid >> 5;
+  const long long t0 = (long long)blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
+  for (long long tl = t0; tl < t1; ++tl) {
+    int b, z0, y0, x0; decode_tile(tl, ntx, nty, ntz, b, z0, y0, x0);
+    const bf16* Sb = reinterpret_cast<const bf16*>(S.p) + (long long)b * S.bstride;
+    __syncthreads();
+    for (int i = tid; i < WZ * WY * HXw; i += 256) {
+      const int hx = i % HXw; const int r = i / HXw; const int hy = r % WY; const int hz = r / WY;
+      const int z = z0 + hz + dz - a.pad[0] + S.shift[0], y = y0 + hy + dy - a.pad[1] + S.shift[1], x = x0 + hx - a.pad[2] + S.shift[2];
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
+        q = __ldg(reinterpret_cast<const uint4*>(Sb + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff + ca0));
+      tile[i] = q;
+    }
+    __syncthreads();
+    const int py = y0 + ly, px = x0 + lx;
+    if (py < a.L[1] && px < a.L[2]) {
 #pragma unroll
-    for (int tp = 0; tp < KX; ++tp) {
-      const int tx = tx0 + tp;
-      if (tx < 0 || tx >= S.X) continue;
-      float sv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(S.p) + so + (long long)tp * S.C)), sv);
+      for (int j = 0; j < WZ; ++j) {
+        const int pz = z0 + j;
+        if (pz >= a.L[0]) break;
+        const long long po = (long long)b * a.p_bstride + ((((long long)pz + a.p_off[0]) * a.PY + py + a.p_off[1]) * a.PX + px + a.p_off[2]) * a.p_C + a.p_coff;
+        const float pv = (a.p_dtype == DT_BF16) ? bf2f(reinterpret_cast<const bf16*>(a.P)[po]) : reinterpret_cast<const float*>(a.P)[po];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[tp][c] = fmaf(sv[c], pv, acc[tp][c]);
+        for (int tp = 0; tp < 3; ++tp) {
+          float sv[8]; unpack8(tile[(j * WY + ly) * HXw + lx + tp], sv);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[tp][c] = fmaf(sv[c], pv, acc[tp][c]);
+        }
+      }
     }
   }
-  const int lane = threadIdx.x & 31;
+  const int lane = tid & 31;
 #pragma unroll
-  for (int tp = 0; tp < KX; ++tp)
+  for (int tp = 0; tp < 3; ++tp)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      float s = acc[tp][c];
+      float sum = acc[tp][c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == ((tp * 8 + c) & 31) && ca0 + c < a.Ca && s != 0.f)
-        atomicAdd(a.dw + (long long)((dz * a.k[1] + dy) * KX + tp) * a.ws_tap + (long long)(ca0 + c) * a.ws_a, s);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == ((tp * 8 + c) & 31) && ca0 + c < a.Ca && sum != 0.f)
+        atomicAdd(a.dw + (long long)((dz * 3 + dy) * 3 + tp) * a.ws_tap + (long long)(ca0 + c) * a.ws_a, sum);
     }
 }
 
@@ -125,7 +155,7 @@ __global__ void __launch_bounds__(128) wgrad_cout1_kernel(const WgradArgs a) {
 
 bool wgrad_c1_supported(const WgradArgs& w) {
   for (int i = 0; i < 3; ++i) if (w.stride[i] != 1) return false;
-  if (w.k[1] != 3 || w.k[2] != 3) return false;
+  if (w.k[1] != 3 || w.k[2] != 3 || (w.k[0] != 3 && w.k[0] != 1)) return false;
   if (w.Ca == 1 && w.Cb >= 8 && w.Cb % 8 == 0 && w.p_C % 8 == 0 && w.p_coff % 8 == 0) return true;
   if (w.Cb == 1 && w.Ca >= 8 && w.Ca % 8 == 0 && w.S.dtype == DT_BF16 && w.S.C % 8 == 0 && w.S.coff % 8 == 0 && !w.S.origins) return true;
   return false;
@@ -135,18 +165,17 @@ cudaError_t launch_wgrad_c1(const WgradArgs& w_in, cudaStream_t st) {
   WgradArgs a = w_in;
   a.nvox = (long long)a.B * a.L[0] * a.L[1] * a.L[2];
   if (a.nvox == 0) return cudaSuccess;
-  long long per = 128 * 48;                       // ~48 positions per thread amortise the shuffle reduction
-  long long gx = (a.nvox + per - 1) / per;
-  if (gx > 148 * 8) { gx = 148 * 8; per = (a.nvox + gx - 1) / gx; }
-  a.vox_per_cta = per;
-  gx = (a.nvox + per - 1) / per;
-  if (a.Ca == 1) {
-    dim3 grid((unsigned)gx, a.k[0], a.Cb / 8);
-    wgrad_cin1_kernel<9><<<grid, 128, 0, st>>>(a);
-  } else {
-    dim3 grid((unsigned)gx, a.k[0] * a.k[1], a.Ca / 8);
-    wgrad_cout1_kernel<3><<<grid, 128, 0, st>>>(a);
-  }
+  const int ntx = (a.L[2] + WX - 1) / WX, nty = (a.L[1] + WY - 1) / WY, ntz = (a.L[0] + WZ - 1) / WZ;
+  const long long ntiles = (long long)a.B * ntx * nty * ntz;
+  const int gy = (a.Ca == 1) ? a.k[0] : a.k[0] * a.k[1];
+  const int gz = (a.Ca == 1) ? a.Cb / 8 : a.Ca / 8;
+  long long gx = (148 * 6 + gy * gz - 1) / (gy * gz);          // ~6 CTAs per SM in total
+  if (gx > ntiles) gx = ntiles;
+  const long long per = (ntiles + gx - 1) / gx;
+  gx = (ntiles + per - 1) / per;
+  dim3 grid((unsigned)gx, gy, gz);
+  if (a.Ca == 1) wgrad_cin1_kernel<<<grid, 256, 0, st>>>(a, ntx, nty, ntz, ntiles, per);
+  else wgrad_cout1_kernel<<<grid, 256, 0, st>>>(a, ntx, nty, ntz, ntiles, per);
   ++g_tem_launches;
   return cudaGetLastError();
 }

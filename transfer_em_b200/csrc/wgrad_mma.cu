@@ -50,37 +50,46 @@ __device__ __forceinline__ void mma_bf16(float* d, uint32_t a0, uint32_t a1, uin
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint32_t sbuf, uint32_t pbuf, int tid, int nthreads) {
+// Row-wise staging: a halo row (fixed z,y) is HX voxels x Ca channels of contiguous global memory, copied as 16 B
+// chunks into the 8-channel planes; one warp per row, so the only per-chunk index math is j / planes, j % planes.
+__device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint32_t sbuf, uint32_t pbuf, int warp, int lane) {
   long long t = tile;
   const int tx = (int)(t % a.ntx); t /= a.ntx;
   const int ty = (int)(t % a.nty); t /= a.nty;
   const int tz = (int)(t % a.ntz); t /= a.ntz;
   const int b = (int)t;
   const int px0 = tx * TXW, py0 = ty * a.TY, pz0 = tz * a.TZ;
-  // S halo: voxel (hz,hy,hx) <-> S coordinate s*p0 - pad + h + shift
   const int hvox = a.HZ * a.HY * a.HX;
   const int pa = a.Ca >> 3;
   const int sz0 = pz0 * a.stride[0] - a.pad[0] + a.shift[0], sy0 = py0 * a.stride[1] - a.pad[1] + a.shift[1], sx0 = px0 * a.stride[2] - a.pad[2] + a.shift[2];
   const bf16* Sb = a.S + (long long)b * a.s_bstride;
-  for (int i = tid; i < hvox * pa; i += nthreads) {
-    const int plane = i % pa; const int v = i / pa;
-    const int hx = v % a.HX; const int r = v / a.HX; const int hy = r % a.HY; const int hz = r / a.HY;
-    const int z = sz0 + hz, y = sy0 + hy, x = sx0 + hx;
-    const bool ok = z >= 0 && z < a.SZ && y >= 0 && y < a.SY && x >= 0 && x < a.SX;
-    const bf16* src = ok ? Sb + (((long long)z * a.SY + y) * a.SX + x) * a.Ca + plane * 8 : a.S;
-    cp_async16(sbuf + (uint32_t)(plane * hvox + v) * 16u, src, ok);
+  const int srow_chunks = a.HX * pa;
+  for (int row = warp; row < a.HZ * a.HY; row += kWarps) {
+    const int hz = row / a.HY, hy = row % a.HY;
+    const int z = sz0 + hz, y = sy0 + hy;
+    const bool rowok = z >= 0 && z < a.SZ && y >= 0 && y < a.SY;
+    const bf16* rp = Sb + (((long long)z * a.SY + y) * a.SX + sx0) * a.Ca;
+    for (int j = lane; j < srow_chunks; j += 32) {
+      const int hx = j / pa, plane = j - hx * pa;
+      const int x = sx0 + hx;
+      const bool ok = rowok && x >= 0 && x < a.SX;
+      cp_async16(sbuf + (uint32_t)(plane * hvox + row * a.HX + hx) * 16u, ok ? (const void*)(rp + (long long)j * 8) : (const void*)a.S, ok);
+    }
   }
-  // P tile: position (pz,py,px) <-> P coordinate p + p_off, zero outside the logical extent
   const int tvox = a.TZ * a.TY * TXW;
   const int pb = a.Cb >> 3;
   const bf16* Pb = a.P + (long long)b * a.p_bstride;
-  for (int i = tid; i < tvox * pb; i += nthreads) {
-    const int plane = i % pb; const int v = i / pb;
-    const int px = v % TXW; const int r = v / TXW; const int py = r % a.TY; const int pz = r / a.TY;
-    const int z = pz0 + pz, y = py0 + py, x = px0 + px;
-    const bool ok = z < a.L[0] && y < a.L[1] && x < a.L[2];
-    const bf16* src = ok ? Pb + (((long long)(z + a.p_off[0]) * a.PY + y + a.p_off[1]) * a.PX + x + a.p_off[2]) * a.Cb + plane * 8 : a.P;
-    cp_async16(pbuf + (uint32_t)(plane * tvox + v) * 16u, src, ok);
+  const int prow_chunks = TXW * pb;
+  for (int row = warp; row < a.TZ * a.TY; row += kWarps) {
+    const int pz = row / a.TY, py = row % a.TY;
+    const int z = pz0 + pz, y = py0 + py;
+    const bool rowok = z < a.L[0] && y < a.L[1];
+    const bf16* rp = Pb + ((((long long)z + a.p_off[0]) * a.PY + y + a.p_off[1]) * a.PX + px0 + a.p_off[2]) * a.Cb;
+    for (int j = lane; j < prow_chunks; j += 32) {
+      const int px = j / pb, plane = j - px * pb;
+      const bool ok = rowok && (px0 + px) < a.L[2];
+      cp_async16(pbuf + (uint32_t)(plane * tvox + row * TXW + px) * 16u, ok ? (const void*)(rp + (long long)j * 8) : (const void*)a.P, ok);
+    }
   }
 }
 
@@ -120,12 +129,12 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
 
   const long long t_begin = (long long)blockIdx.x * a.tiles_per_cta;
   const long long t_end = min(t_begin + a.tiles_per_cta, a.ntiles);
-  if (t_begin < t_end) stage_tile(a, t_begin, base, base + a.s_bytes, tid, kWarps * 32);
+  if (t_begin < t_end) stage_tile(a, t_begin, base, base + a.s_bytes, warp, lane);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   for (long long t = t_begin; t < t_end; ++t) {
     const int cur = (int)((t - t_begin) & 1);
-    if (t + 1 < t_end) stage_tile(a, t + 1, base + (cur ^ 1) * buf_bytes, base + (cur ^ 1) * buf_bytes + a.s_bytes, tid, kWarps * 32);
+    if (t + 1 < t_end) stage_tile(a, t + 1, base + (cur ^ 1) * buf_bytes, base + (cur ^ 1) * buf_bytes + a.s_bytes, warp, lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
@@ -194,14 +203,17 @@ cudaError_t launch_wgrad_mma(const WgradArgs& w, cudaStream_t st) {
   a.ntiles_out = a.Mtiles * a.NB;
   if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
   // tile: shrink until two buffers fit in ~96 KB
-  int TZ = (w.L[0] >= 2) ? 2 : 1, TY = (w.L[1] >= 4) ? 4 : (w.L[1] >= 2 ? 2 : 1);
+  int TZ = (w.L[0] >= 4) ? 4 : (w.L[0] >= 2 ? 2 : 1), TY = (w.L[1] >= 8) ? 8 : (w.L[1] >= 4 ? 4 : (w.L[1] >= 2 ? 2 : 1));
   auto bytes = [&](int tz, int ty, int& hz, int& hy, int& hx, int& sb, int& pb) {
     hz = (tz - 1) * w.stride[0] + w.k[0]; hy = (ty - 1) * w.stride[1] + w.k[1]; hx = (TXW - 1) * w.stride[2] + w.k[2];
     sb = ((hz * hy * hx * w.Ca * 2) + 127) & ~127; pb = ((tz * ty * TXW * w.Cb * 2) + 127) & ~127;
     return 2 * (sb + pb);
   };
   int hz, hy, hx, sb, pb;
-  while (bytes(TZ, TY, hz, hy, hx, sb, pb) > 96 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ = 1; else TY >>= 1; }
+  while (bytes(TZ, TY, hz, hy, hx, sb, pb) > 96 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
+  // keep enough tiles to occupy the machine
+  auto ntl = [&](int tz, int ty) { return (long long)w.B * ((w.L[0] + tz - 1) / tz) * ((w.L[1] + ty - 1) / ty) * ((w.L[2] + TXW - 1) / TXW); };
+  while (ntl(TZ, TY) < 2 * 148 && (TZ > 1 || TY > 2)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
   const int smem = bytes(TZ, TY, hz, hy, hx, sb, pb);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   a.TZ = TZ; a.TY = TY; a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.p_bytes = pb;
