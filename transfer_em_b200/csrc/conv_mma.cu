@@ -120,13 +120,21 @@ __global__ void __launch_bounds__(kWarpsC * 32) conv_mma_kernel(const CmArgs a) 
     if (cc) __syncthreads();
     // ---- stage the input halo for this channel chunk as 8-channel planes
     const int planes = cin8 ? 1 : 2;
-    for (int i = tid; i < hvox * planes; i += kWarpsC * 32) {
-      const int pl = i % planes; const int v = i / planes;
-      const int hx = v % a.HX; const int rr = v / a.HX; const int hy = rr % a.HY; const int hz = rr / a.HY;
-      const int z = org[0] + hz + a.shift[0], y = org[1] + hy + a.shift[1], x = org[2] + hx + a.shift[2];
-      const bool ok = z >= 0 && z < a.IZ && y >= 0 && y < a.IY && x >= 0 && x < a.IX;
-      const bf16* src = ok ? inb + (((long long)z * a.IY + y) * a.IX + x) * a.Cin + cc * 16 + pl * 8 : a.in;
-      cp16(sbuf + (uint32_t)(pl * hvox + v) * 16u, src, ok);
+    {
+      // row-wise: a halo row (fixed z,y) is HX voxels x Cin channels of contiguous global memory
+      const int row_chunks = a.HX * planes;
+      for (int row = warp; row < a.HZ * a.HY; row += kWarpsC) {
+        const int hz = row / a.HY, hy = row - hz * a.HY;
+        const int z = org[0] + hz + a.shift[0], y = org[1] + hy + a.shift[1], xb = org[2] + a.shift[2];
+        const bool rowok = z >= 0 && z < a.IZ && y >= 0 && y < a.IY;
+        const bf16* rp = inb + (((long long)z * a.IY + y) * a.IX + xb) * a.Cin + cc * 16;
+        for (int j = lane; j < row_chunks; j += 32) {
+          const int hx = cin8 ? j : (j >> 1), pl = cin8 ? 0 : (j & 1);
+          const int x = xb + hx;
+          const bool ok = rowok && x >= 0 && x < a.IX;
+          cp16(sbuf + (uint32_t)(pl * hvox + row * a.HX + hx) * 16u, ok ? (const void*)(rp + (long long)hx * a.Cin + pl * 8) : (const void*)a.in, ok);
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- stage the weights of this chunk: [kstep][n][16 k] bf16 (k = 16 channels, or 2 taps x 8 channels)

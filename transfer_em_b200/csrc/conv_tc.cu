@@ -25,7 +25,7 @@ namespace {
 constexpr int TX = 8, TY = 16, HX = TX + 2, HY = TY + 2;
 constexpr int PLANE_BYTES = HY * HX * 16;          // 2880: one 8-channel plane of a halo slice
 constexpr int PLANE_STRIDE = 2944;                 // padded to a multiple of 128 B (TMA destination alignment)
-constexpr int RING = 5;
+constexpr int RING_MAX = 12;
 constexpr int kTcThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,7 +89,7 @@ struct TcArgs {
   int spd;                     // k-steps (K=16 MMAs) per dz
   int cin8;                    // 1 when Cin == 8 (tap-pair k-steps)
   const bf16* wpacked; int wbytes;
-  int ntx, nty, nzc, zc;
+  int ntx, nty, nzc, zc, ring;
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
   float slope;
@@ -102,7 +102,8 @@ template <int NPAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[RING], empty_bar[RING], w_bar, tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t full_bar[RING_MAX], empty_bar[RING_MAX], w_bar, tfull_bar[2], tempty_bar[2];
+  const int RING = a.ring;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -341,7 +342,7 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
   const int steps = 3 * (cin == 8 ? 5 : 9 * (cin / 16));
   const int npad = a.Cout <= 16 ? 16 : 32;
-  const size_t smem = (((size_t)steps * npad * 32 + 1023) & ~(size_t)1023) + (size_t)RING * (cin / 8) * PLANE_STRIDE + 1024;
+  const size_t smem = (((size_t)steps * npad * 32 + 1023) & ~(size_t)1023) + (size_t)5 * (cin / 8) * PLANE_STRIDE + 1024;
   if (smem > 200 * 1024) return false;
   if (a.conv_off[0] || a.conv_off[1] || a.conv_off[2]) return false;
   return get_encode() != nullptr;
@@ -392,7 +393,12 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t 
   if (a.C1) { if (!make_map(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C)) return cudaErrorInvalidValue; }
   else m1 = m0;
   const int npad = a.Cout <= 16 ? 16 : 32;
-  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)RING * (cin / 8) * PLANE_STRIDE + 1024;
+  // ring depth: as many halo slices in flight as ~48 KB allow (TMA latency >> per-slice MMA time), 5..12
+  int ring = (int)((48 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));
+  if (ring > RING_MAX) ring = RING_MAX;
+  if (ring < 5) ring = 5;
+  t.ring = ring;
+  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)ring * (cin / 8) * PLANE_STRIDE + 1024;
   const unsigned grid = (unsigned)(cols * t.nzc);
   static bool attr16 = false, attr32 = false;
   if (npad == 16) {

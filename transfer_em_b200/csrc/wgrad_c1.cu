@@ -50,12 +50,17 @@ __global__ void __launch_bounds__(256) wgrad_cin1_kernel(const WgradArgs a, cons
     __syncthreads();
     const float fill = (a.use_lut && S.origins) ? lut[0] : 0.f;
     // only the z-planes dz .. dz+WZ-1 of the halo are needed by this CTA
-    for (int i = tid; i < WZ * HYw * HXw; i += 256) {
-      const int hx = i % HXw; const int r = i / HXw; const int hy = r % HYw; const int hz = r / HYw;
-      const int z = z0 + hz + dz - a.pad[0] + S.shift[0] + oz, y = y0 + hy - a.pad[1] + S.shift[1] + oy, x = x0 + hx - a.pad[2] + S.shift[2] + ox;
-      float v = fill;
-      if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X) v = load1(S, sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff, lut);
-      tile[i] = v;
+    for (int row = tid >> 5; row < WZ * HYw; row += 8) {          // one warp per halo row, lanes along x
+      const int hz = row / HYw, hy = row - hz * HYw;
+      const int z = z0 + hz + dz - a.pad[0] + S.shift[0] + oz, y = y0 + hy - a.pad[1] + S.shift[1] + oy, xb = x0 - a.pad[2] + S.shift[2] + ox;
+      const bool rowok = z >= 0 && z < S.Z && y >= 0 && y < S.Y;
+      const long long rbase = sbase + (((long long)z * S.Y + y) * S.X + xb) * S.C + S.coff;
+      for (int hx = tid & 31; hx < HXw; hx += 32) {
+        const int x = xb + hx;
+        float v = fill;
+        if (rowok && x >= 0 && x < S.X) v = load1(S, rbase + (long long)hx * S.C, lut);
+        tile[row * HXw + hx] = v;
+      }
     }
     __syncthreads();
     const int py = y0 + ly, px = x0 + lx;

@@ -27,7 +27,7 @@ struct WgArgs {
   const bf16* P; int PZ, PY, PX; int p_off[3]; long long p_bstride;
   int Ca, Cb, B, L[3], k[3], stride[3], pad[3];
   float* dw; long long ws_tap, ws_a, ws_b;
-  int TZ, TY;                       // tile (TZ x TY x 16 positions)
+  int TZ, TY, ty_sh;                // tile (TZ x TY x 16 positions), TY a power of two
   int HZ, HY, HX;                   // halo extents
   int ntz, nty, ntx; long long ntiles; long long tiles_per_cta;
   int Mtiles, NB, ntap, ntiles_out; // output tiling
@@ -60,7 +60,7 @@ __device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint
   const int b = (int)t;
   const int px0 = tx * TXW, py0 = ty * a.TY, pz0 = tz * a.TZ;
   const int hvox = a.HZ * a.HY * a.HX;
-  const int pa = a.Ca >> 3;
+  const int pa = a.Ca >> 3, pa_sh = 31 - __clz(pa);          // planes are powers of two: no integer division per chunk
   const int sz0 = pz0 * a.stride[0] - a.pad[0] + a.shift[0], sy0 = py0 * a.stride[1] - a.pad[1] + a.shift[1], sx0 = px0 * a.stride[2] - a.pad[2] + a.shift[2];
   const bf16* Sb = a.S + (long long)b * a.s_bstride;
   const int srow_chunks = a.HX * pa;
@@ -70,23 +70,23 @@ __device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint
     const bool rowok = z >= 0 && z < a.SZ && y >= 0 && y < a.SY;
     const bf16* rp = Sb + (((long long)z * a.SY + y) * a.SX + sx0) * a.Ca;
     for (int j = lane; j < srow_chunks; j += 32) {
-      const int hx = j / pa, plane = j - hx * pa;
+      const int hx = j >> pa_sh, plane = j & (pa - 1);
       const int x = sx0 + hx;
       const bool ok = rowok && x >= 0 && x < a.SX;
       cp_async16(sbuf + (uint32_t)(plane * hvox + row * a.HX + hx) * 16u, ok ? (const void*)(rp + (long long)j * 8) : (const void*)a.S, ok);
     }
   }
   const int tvox = a.TZ * a.TY * TXW;
-  const int pb = a.Cb >> 3;
+  const int pb = a.Cb >> 3, pb_sh = 31 - __clz(pb);
   const bf16* Pb = a.P + (long long)b * a.p_bstride;
   const int prow_chunks = TXW * pb;
   for (int row = warp; row < a.TZ * a.TY; row += kWarps) {
-    const int pz = row / a.TY, py = row % a.TY;
+    const int pz = row >> a.ty_sh, py = row & (a.TY - 1);
     const int z = pz0 + pz, y = py0 + py;
     const bool rowok = z < a.L[0] && y < a.L[1];
     const bf16* rp = Pb + ((((long long)z + a.p_off[0]) * a.PY + y + a.p_off[1]) * a.PX + px0 + a.p_off[2]) * a.Cb;
     for (int j = lane; j < prow_chunks; j += 32) {
-      const int px = j / pb, plane = j - px * pb;
+      const int px = j >> pb_sh, plane = j & (pb - 1);
       const bool ok = rowok && (px0 + px) < a.L[2];
       cp_async16(pbuf + (uint32_t)(plane * tvox + row * TXW + px) * 16u, ok ? (const void*)(rp + (long long)j * 8) : (const void*)a.P, ok);
     }
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) 
     __syncthreads();
     const uint32_t sbuf = base + cur * buf_bytes, pbuf = sbuf + a.s_bytes;
     for (int row = rpart; row < a.TZ * a.TY; row += a.rsplit) {
-      const int pz = row / a.TY, py = row % a.TY;
+      const int pz = row >> a.ty_sh, py = row & (a.TY - 1);
       const int rowbase = (pz * a.stride[0] * a.HY + py * a.stride[1]) * a.HX;
       uint32_t b0 = 0, b1 = 0; int bcur = -1;
 #pragma unroll
@@ -186,6 +186,7 @@ bool wgrad_mma_supported(const WgradArgs& w) {
   if (w.S.origins || w.use_lut) return false;
   if (w.Ca % 8 || w.Cb % 8 || w.Ca < 8 || w.Cb < 8) return false;
   if (!(w.Ca == 8 || w.Ca % 16 == 0)) return false;
+  if (((w.Ca >> 3) & ((w.Ca >> 3) - 1)) || ((w.Cb >> 3) & ((w.Cb >> 3) - 1))) return false;   // 8-channel plane counts are powers of two
   if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
   for (int i = 0; i < 3; ++i) if (w.stride[i] > 2) return false;
   return true;
@@ -216,7 +217,7 @@ cudaError_t launch_wgrad_mma(const WgradArgs& w, cudaStream_t st) {
   while (ntl(TZ, TY) < 2 * 148 && (TZ > 1 || TY > 2)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
   const int smem = bytes(TZ, TY, hz, hy, hx, sb, pb);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  a.TZ = TZ; a.TY = TY; a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.p_bytes = pb;
+  a.TZ = TZ; a.TY = TY; a.ty_sh = (TY == 8) ? 3 : (TY == 4 ? 2 : (TY == 2 ? 1 : 0)); a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.p_bytes = pb;
   a.ntz = (w.L[0] + TZ - 1) / TZ; a.nty = (w.L[1] + TY - 1) / TY; a.ntx = (w.L[2] + TXW - 1) / TXW;
   a.ntiles = (long long)w.B * a.ntz * a.nty * a.ntx;
   a.G = (a.ntiles_out + kTPW - 1) / kTPW;
