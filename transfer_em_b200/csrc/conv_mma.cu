@@ -83,19 +83,20 @@ __global__ void __launch_bounds__(kWarpsC * 32) conv_mma_kernel(const CmArgs a) 
       org[ax] = p0[ax] + (par[ax] + a.pad[ax] - d0[ax]) / s - (cnt[ax] - 1);
     }
   }
-  if (tid == 0) {
-    int n = 0;
-    for (int mz = 0; mz < cnt[0]; ++mz) for (int my = 0; my < cnt[1]; ++my) for (int mx = 0; mx < cnt[2]; ++mx) {
+  {
+    // one thread per local tap
+    const int n = cnt[0] * cnt[1] * cnt[2];
+    if (tid < n) {
+      const int mx = tid % cnt[2], my = (tid / cnt[2]) % cnt[1], mz = tid / (cnt[2] * cnt[1]);
       int bz, by, bx, dz, dy, dx;
       if (a.form == 0) { bz = dz = mz; by = dy = my; bx = dx = mx; }
       else { dz = d0[0] + a.stride[0] * mz; dy = d0[1] + a.stride[1] * my; dx = d0[2] + a.stride[2] * mx;
              bz = cnt[0] - 1 - mz; by = cnt[1] - 1 - my; bx = cnt[2] - 1 - mx; }
-      toff[n] = (bz * a.HY + by) * a.HX + bx;
-      wtap[n] = (dz * a.k[1] + dy) * a.k[2] + dx;
-      ++n;
+      toff[tid] = (bz * a.HY + by) * a.HX + bx;
+      wtap[tid] = (dz * a.k[1] + dy) * a.k[2] + dx;
+      if (tid == n - 1) { toff[n] = toff[tid]; wtap[n] = -1; }     // dummy partner for an odd tap count (Cin == 8)
     }
-    toff[n] = toff[n > 0 ? n - 1 : 0]; wtap[n] = -1;     // dummy partner for an odd tap count (Cin == 8)
-    ntap_s = n;
+    if (tid == 0) ntap_s = n;
   }
   __syncthreads();
   const int ntap = ntap_s;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kWarpsC * 32) conv_mma_kernel(const CmArgs a) 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- stage the weights of this chunk: [kstep][n][16 k] bf16 (k = 16 channels, or 2 taps x 8 channels)
+#pragma unroll 4
     for (int i = tid; i < ksteps * npad * 16; i += kWarpsC * 32) {
       const int kk = i & 15; const int n = (i >> 4) % npad; const int ks = (i >> 4) / npad;
       int tap, ci;

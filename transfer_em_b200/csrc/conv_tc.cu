@@ -99,7 +99,7 @@ struct TcArgs {
 };
 
 template <int NPAD>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, (NPAD == 16) ? 4 : 3)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[RING_MAX], empty_bar[RING_MAX], w_bar, tfull_bar[2], tempty_bar[2];
@@ -143,15 +143,16 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     if (lane == 0) {
       mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
       bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
+      int slot = 0; uint32_t ph = 0;                       // ring position kept incrementally (no runtime division)
       for (int s = 0; s < nslices; ++s) {
-        const int slot = s % RING;
-        mbar_wait(&empty_bar[slot], (((uint32_t)(s / RING)) & 1u) ^ 1u);
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * PLANE_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         for (int p = 0; p < a.planes0; ++p)
           tma_load_5d(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], p * 8, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
         for (int p = 0; p < a.planes1; ++p)
           tma_load_5d(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], p * 8, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
+        if (++slot == RING) { slot = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -160,16 +161,17 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       mbar_wait(&w_bar, 0);
       const uint32_t wbase = smem_u32(wsm);
       const uint32_t rbase = smem_u32(ring);
-      int waited = 0;
+      int waited = 0, wslot = 0, zslot = 0; uint32_t wph = 0;
       for (int zo = 0; zo < nz; ++zo) {
-        while (waited < zo + 3) { mbar_wait(&full_bar[waited % RING], ((uint32_t)(waited / RING)) & 1u); ++waited; }
+        while (waited < zo + 3) { mbar_wait(&full_bar[wslot], wph); ++waited; if (++wslot == RING) { wslot = 0; wph ^= 1u; } }
         mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NPAD;
         uint32_t acc = 0;
         int step = 0;
         for (int dz = 0; dz < 3; ++dz) {
-          const uint32_t sbase = rbase + (uint32_t)((zo + dz) % RING) * slot_bytes;
+          int sl = zslot + dz; if (sl >= RING) sl -= RING;
+          const uint32_t sbase = rbase + (uint32_t)sl * slot_bytes;
           if (a.cin8) {
             // Cin == 8: one plane; a K=16 step covers two taps (LBO = distance between the taps), the 10th tap is a
             // zero-weight dummy
@@ -195,7 +197,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           }
         }
         umma_commit(&tfull_bar[zo & 1]);     // accumulator ready for the epilogue
-        umma_commit(&empty_bar[zo % RING]);  // input slice zo is no longer needed
+        umma_commit(&empty_bar[zslot]);      // input slice zo is no longer needed
+        if (++zslot == RING) zslot = 0;
       }
     }
   } else {
@@ -393,8 +396,8 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t 
   if (a.C1) { if (!make_map(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C)) return cudaErrorInvalidValue; }
   else m1 = m0;
   const int npad = a.Cout <= 16 ? 16 : 32;
-  // ring depth: as many halo slices in flight as ~48 KB allow (TMA latency >> per-slice MMA time), 5..12
-  int ring = (int)((48 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));
+  // ring depth 5..12 within ~16 KB: measured, occupancy (CTAs per SM) hides TMA latency better than a deeper ring
+  int ring = (int)((16 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));
   if (ring > RING_MAX) ring = RING_MAX;
   if (ring < 5) ring = 5;
   t.ring = ring;

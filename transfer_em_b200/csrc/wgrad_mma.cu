@@ -93,7 +93,7 @@ __device__ __forceinline__ void stage_tile(const WgArgs& a, long long tile, uint
   }
 }
 
-__global__ void __launch_bounds__(kWarps * 32) wgrad_mma_kernel(const WgArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 2) wgrad_mma_kernel(const WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -211,7 +211,7 @@ cudaError_t launch_wgrad_mma(const WgradArgs& w, cudaStream_t st) {
     return 2 * (sb + pb);
   };
   int hz, hy, hx, sb, pb;
-  while (bytes(TZ, TY, hz, hy, hx, sb, pb) > 96 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
+  while (bytes(TZ, TY, hz, hy, hx, sb, pb) > 100 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
   // keep enough tiles to occupy the machine
   auto ntl = [&](int tz, int ty) { return (long long)w.B * ((w.L[0] + tz - 1) / tz) * ((w.L[1] + ty - 1) / ty) * ((w.L[2] + TXW - 1) / TXW); };
   while (ntl(TZ, TY) < 2 * 148 && (TZ > 1 || TY > 2)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
