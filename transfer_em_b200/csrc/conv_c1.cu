@@ -47,13 +47,30 @@ __global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const 
   int oz = 0, oy = 0, ox = 0; long long sbase = (long long)b * S.bstride;
   if (S.origins) { oz = S.origins[b * 3]; oy = S.origins[b * 3 + 1]; ox = S.origins[b * 3 + 2]; sbase = 0; }
   const float fill = (a.use_lut && S.origins) ? lut[0] : 0.f;
-  for (int i = tid; i < HZc * HYc * HXc; i += 256) {
-    const int hx = i % HXc; const int r = i / HXc; const int hy = r % HYc; const int hz = r / HYc;
-    const int z = z0 + hz - pad + S.shift[0] + oz, y = y0 + hy - pad + S.shift[1] + oy, x = x0 + hx - pad + S.shift[2] + ox;
-    float v = fill;
-    if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
-      v = ld1(S, sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff, lut);
-    tile[i] = v;
+  {
+    // all loads of a thread are issued before any is consumed
+    constexpr int NS = (HZc * HYc * HXc + 255) / 256;
+    float raw[NS]; bool okv[NS];
+    const int zb = z0 - pad + S.shift[0] + oz, yb = y0 - pad + S.shift[1] + oy, xb = x0 - pad + S.shift[2] + ox;
+#pragma unroll
+    for (int sI = 0; sI < NS; ++sI) {
+      const int i = tid + sI * 256;
+      const int hx = i % HXc, r = i / HXc, hy = r % HYc, hz = r / HYc;
+      const int z = zb + hz, y = yb + hy, x = xb + hx;
+      okv[sI] = i < HZc * HYc * HXc && z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X;
+      const long long off = sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff;
+      raw[sI] = 0.f;
+      if (okv[sI]) {
+        if (S.dtype == DT_U8) raw[sI] = (float)reinterpret_cast<const uint8_t*>(S.p)[off];
+        else if (S.dtype == DT_BF16) raw[sI] = bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
+        else raw[sI] = reinterpret_cast<const float*>(S.p)[off];
+      }
+    }
+#pragma unroll
+    for (int sI = 0; sI < NS; ++sI) {
+      const int i = tid + sI * 256;
+      if (i < HZc * HYc * HXc) tile[i] = okv[sI] ? ((S.dtype == DT_U8) ? lut[(int)raw[sI]] : raw[sI]) : fill;
+    }
   }
   __syncthreads();
   const int lx = tid & 31, ly = tid >> 5;        // 32 x 8 threads, 4 voxels in z each

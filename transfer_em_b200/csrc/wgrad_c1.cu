@@ -50,16 +50,29 @@ __global__ void __launch_bounds__(256) wgrad_cin1_kernel(const WgradArgs a, cons
     __syncthreads();
     const float fill = (a.use_lut && S.origins) ? lut[0] : 0.f;
     // only the z-planes dz .. dz+WZ-1 of the halo are needed by this CTA
-    for (int row = tid >> 5; row < WZ * HYw; row += 8) {          // one warp per halo row, lanes along x
-      const int hz = row / HYw, hy = row - hz * HYw;
-      const int z = z0 + hz + dz - a.pad[0] + S.shift[0] + oz, y = y0 + hy - a.pad[1] + S.shift[1] + oy, xb = x0 - a.pad[2] + S.shift[2] + ox;
-      const bool rowok = z >= 0 && z < S.Z && y >= 0 && y < S.Y;
-      const long long rbase = sbase + (((long long)z * S.Y + y) * S.X + xb) * S.C + S.coff;
-      for (int hx = tid & 31; hx < HXw; hx += 32) {
-        const int x = xb + hx;
-        float v = fill;
-        if (rowok && x >= 0 && x < S.X) v = load1(S, rbase + (long long)hx * S.C, lut);
-        tile[row * HXw + hx] = v;
+    {
+      // all loads of a thread are issued before any is consumed (6 independent requests in flight per thread)
+      constexpr int NS = (WZ * HYw * HXw + 255) / 256;
+      float raw[NS]; bool okv[NS];
+      const int zb = z0 + dz - a.pad[0] + S.shift[0] + oz, yb = y0 - a.pad[1] + S.shift[1] + oy, xb = x0 - a.pad[2] + S.shift[2] + ox;
+#pragma unroll
+      for (int sI = 0; sI < NS; ++sI) {
+        const int i = tid + sI * 256;
+        const int hx = i % HXw, r = i / HXw, hy = r % HYw, hz = r / HYw;
+        const int z = zb + hz, y = yb + hy, x = xb + hx;
+        okv[sI] = i < WZ * HYw * HXw && z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X;
+        const long long off = sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff;
+        raw[sI] = 0.f;
+        if (okv[sI]) {
+          if (S.dtype == DT_U8) raw[sI] = (float)reinterpret_cast<const uint8_t*>(S.p)[off];
+          else if (S.dtype == DT_BF16) raw[sI] = bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
+          else raw[sI] = reinterpret_cast<const float*>(S.p)[off];
+        }
+      }
+#pragma unroll
+      for (int sI = 0; sI < NS; ++sI) {
+        const int i = tid + sI * 256;
+        if (i < WZ * HYw * HXw) tile[i] = okv[sI] ? ((S.dtype == DT_U8) ? lut[(int)raw[sI]] : raw[sI]) : fill;
       }
     }
     __syncthreads();
@@ -86,7 +99,9 @@ __global__ void __launch_bounds__(256) wgrad_cin1_kernel(const WgradArgs a, cons
       }
     }
   }
-  const int lane = tid & 31;
+  // warp shuffle reduction, then one partial per warp in shared memory, then ONE atomic per output per CTA
+  __shared__ float red[8][72];
+  const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
@@ -94,9 +109,16 @@ __global__ void __launch_bounds__(256) wgrad_cin1_kernel(const WgradArgs a, cons
       float sum = acc[tp][c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == ((tp * 8 + c) & 31) && cb0 + c < a.Cb && sum != 0.f)
-        atomicAdd(a.dw + (long long)(dz * 9 + tp) * a.ws_tap + (long long)(cb0 + c) * a.ws_b, sum);
+      if (lane == ((tp * 8 + c) & 31)) red[wid][tp * 8 + c] = sum;
     }
+  __syncthreads();
+  if (tid < 72) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][tid];
+    const int tp = tid >> 3, c = tid & 7;
+    if (cb0 + c < a.Cb && sum != 0.f) atomicAdd(a.dw + (long long)(dz * 9 + tp) * a.ws_tap + (long long)(cb0 + c) * a.ws_b, sum);
+  }
 }
 
 // Cb == 1 (P fp32 or bf16, one channel).  blockIdx.y = (kz, ky) tap row, blockIdx.z = 8-channel block of S.
@@ -117,13 +139,21 @@ __global__ void __launch_bounds__(256) wgrad_cout1_kernel(const WgradArgs a, con
     int b, z0, y0, x0; decode_tile(tl, ntx, nty, ntz, b, z0, y0, x0);
     const bf16* Sb = reinterpret_cast<const bf16*>(S.p) + (long long)b * S.bstride;
     __syncthreads();
-    for (int i = tid; i < WZ * WY * HXw; i += 256) {
-      const int hx = i % HXw; const int r = i / HXw; const int hy = r % WY; const int hz = r / WY;
-      const int z = z0 + hz + dz - a.pad[0] + S.shift[0], y = y0 + hy + dy - a.pad[1] + S.shift[1], x = x0 + hx - a.pad[2] + S.shift[2];
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
-        q = __ldg(reinterpret_cast<const uint4*>(Sb + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff + ca0));
-      tile[i] = q;
+    {
+      constexpr int NS = (WZ * WY * HXw + 255) / 256;
+      uint4 raw[NS];
+      const int zb = z0 + dz - a.pad[0] + S.shift[0], yb = y0 + dy - a.pad[1] + S.shift[1], xb = x0 - a.pad[2] + S.shift[2];
+#pragma unroll
+      for (int sI = 0; sI < NS; ++sI) {
+        const int i = tid + sI * 256;
+        const int hx = i % HXw, r = i / HXw, hy = r % WY, hz = r / WY;
+        const int z = zb + hz, y = yb + hy, x = xb + hx;
+        raw[sI] = make_uint4(0, 0, 0, 0);
+        if (i < WZ * WY * HXw && z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
+          raw[sI] = __ldg(reinterpret_cast<const uint4*>(Sb + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff + ca0));
+      }
+#pragma unroll
+      for (int sI = 0; sI < NS; ++sI) { const int i = tid + sI * 256; if (i < WZ * WY * HXw) tile[i] = raw[sI]; }
     }
     __syncthreads();
     const int py = y0 + ly, px = x0 + lx;
@@ -143,7 +173,8 @@ __global__ void __launch_bounds__(256) wgrad_cout1_kernel(const WgradArgs a, con
       }
     }
   }
-  const int lane = tid & 31;
+  __shared__ float red[8][24];
+  const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int tp = 0; tp < 3; ++tp)
 #pragma unroll
@@ -151,9 +182,16 @@ __global__ void __launch_bounds__(256) wgrad_cout1_kernel(const WgradArgs a, con
       float sum = acc[tp][c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == ((tp * 8 + c) & 31) && ca0 + c < a.Ca && sum != 0.f)
-        atomicAdd(a.dw + (long long)((dz * 3 + dy) * 3 + tp) * a.ws_tap + (long long)(ca0 + c) * a.ws_a, sum);
+      if (lane == tp * 8 + c) red[wid][tp * 8 + c] = sum;
     }
+  __syncthreads();
+  if (tid < 24) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][tid];
+    const int tp = tid >> 3, c = tid & 7;
+    if (ca0 + c < a.Ca && sum != 0.f) atomicAdd(a.dw + (long long)((dz * 3 + dy) * 3 + tp) * a.ws_tap + (long long)(ca0 + c) * a.ws_a, sum);
+  }
 }
 
 }  // namespace
@@ -174,7 +212,7 @@ cudaError_t launch_wgrad_c1(const WgradArgs& w_in, cudaStream_t st) {
   const long long ntiles = (long long)a.B * ntx * nty * ntz;
   const int gy = (a.Ca == 1) ? a.k[0] : a.k[0] * a.k[1];
   const int gz = (a.Ca == 1) ? a.Cb / 8 : a.Ca / 8;
-  long long gx = (148 * 6 + gy * gz - 1) / (gy * gz);          // ~6 CTAs per SM in total
+  long long gx = (148 * 3 + gy * gz - 1) / (gy * gz);          // ~3 CTAs per SM in total: few, long-lived CTAs keep the atomic tail short
   if (gx > ntiles) gx = ntiles;
   const long long per = (ntiles + gx - 1) / gx;
   gx = (ntiles + per - 1) / per;

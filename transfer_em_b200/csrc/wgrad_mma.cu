@@ -159,22 +159,42 @@ __global__ void __launch_bounds__(kWarps * 32, 2) wgrad_mma_kernel(const WgArgs 
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-  // D fragment: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = (row g+8, cols 2t,2t+1); row = (half, ca), col = cb
-  const int g = lane >> 2, tq = lane & 3;
+  // D fragment: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = (row g+8, cols 2t,2t+1); row = (half, ca), col = cb.
+  // When several warps hold partial sums of the same tiles (row split), they are combined in shared memory first:
+  // same-address global atomics serialise in L2 and were the tail of this kernel.
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem);
+  const bool use_red = a.rsplit > 1 && (size_t)a.ntiles_out * 128 * sizeof(float) <= (size_t)2 * buf_bytes;
+  if (use_red) {
+    for (int i = tid; i < a.ntiles_out * 128; i += kWarps * 32) red[i] = 0.f;
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kTPW; ++i) {
-    const int id = tile0 + i;
-    if (id >= tile_end) continue;
-    const int m = id % a.Mtiles;
+    for (int i = 0; i < kTPW; ++i) {
+      const int id = tile0 + i;
+      if (id >= tile_end) continue;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      int tap, ca;
-      if (a.Ca == 8) { tap = 2 * m + hh; ca = g; if (tap >= a.ntap) continue; }
-      else { const int cb16 = a.Ca >> 4; tap = m / cb16; ca = (2 * (m % cb16) + hh) * 8 + g; }
-      float* dst = a.dw + tap * a.ws_tap + (long long)ca * a.ws_a + (long long)(nblk[i] * 8 + 2 * tq) * a.ws_b;
-      const float v0 = acc[i][2 * hh], v1 = acc[i][2 * hh + 1];
-      if (v0 != 0.f) atomicAdd(dst, v0);
-      if (v1 != 0.f) atomicAdd(dst + a.ws_b, v1);
+      for (int r = 0; r < 4; ++r) if (acc[i][r] != 0.f) atomicAdd(&red[id * 128 + lane * 4 + r], acc[i][r]);
+    }
+    __syncthreads();
+  }
+  auto emit = [&](int id, int ln, int r, float v) {
+    if (v == 0.f) return;
+    const int g = ln >> 2, tq = ln & 3, hh = r >> 1, col = r & 1;
+    const int m = id % a.Mtiles, nb = id / a.Mtiles;
+    int tap, ca;
+    if (a.Ca == 8) { tap = 2 * m + hh; ca = g; if (tap >= a.ntap) return; }
+    else { const int cb16 = a.Ca >> 4; tap = m / cb16; ca = (2 * (m % cb16) + hh) * 8 + g; }
+    atomicAdd(a.dw + tap * a.ws_tap + (long long)ca * a.ws_a + (long long)(nb * 8 + 2 * tq + col) * a.ws_b, v);
+  };
+  if (use_red) {
+    for (int i = tid; i < a.ntiles_out * 128; i += kWarps * 32) emit(i >> 7, (i & 127) >> 2, i & 3, red[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTPW; ++i) {
+      const int id = tile0 + i;
+      if (id >= tile_end) continue;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) emit(id, lane, r, acc[i][r]);
     }
   }
 }
