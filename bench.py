@@ -136,7 +136,7 @@ def cpu_train_sample(steps, warmup, B=1):
             "ms_per_step": dt / steps * 1e3, "host_cpus": os.cpu_count()}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,7 +150,7 @@ def run_reference(args):
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -167,8 +167,14 @@ def main():
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--infer-size", type=int, default=288, help="edge of the tiled-inference request (multiple of 36)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -258,8 +264,12 @@ def main():
     per_launch_ms = t["ms"] / t["count"]
     ach_gbs = t["bytes"] / (per_launch_ms * 1e-3) / 1e9
     ach_tf = t["flops"] / (per_launch_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(tname, {}).get("dram_bytes_per_launch")
     roofline = {"kernel": tname, "bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
-                "traffic": None, "peak_source": pk_src, "avg_launch_ms": per_launch_ms, "launches_per_step": t["count"] / PK,
+                "traffic": traffic, "peak_source": pk_src, "avg_launch_ms": per_launch_ms, "launches_per_step": t["count"] / PK,
                 "share_of_conv_time": t["ms"] / tot_ms, "achieved_tflops": ach_tf,
                 "algorithmic_bytes_per_launch": t["bytes"], "flops_per_launch": t["flops"]}
     step_bytes = sum(v["bytes"] * v["count"] for v in rep.values()) / PK
@@ -316,7 +326,7 @@ def main():
                            "l2": "per-step working set ~1.5 GB of activations >> 126 MB L2; 4 distinct input batches cycled"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
                 "top_kernels": kernels, "cpu_baseline": cpu_baseline, "inference": inference, "losses_last_step": losses}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,6 +10,13 @@ from .cgan import EM2EM
 from .engine import Engine
 
 
+def z_slab_range(nz, rank, world):
+    """Contiguous split of nz z tile-layers over `world` ranks: sizes differ by at most one."""
+    per, rem = divmod(nz, world)
+    zb = rank * per + min(rank, rem)
+    return zb, zb + per + (1 if rank < rem else 0)
+
+
 def _engine_of(model):
     if isinstance(model, Engine):
         return model, NET_G
@@ -39,9 +46,7 @@ def predict_ng_cube(location, start, size, model, meanstd_x, meanstd_y, cloudrun
     if world > 1:
         od2 = od - (od % 6) if (od // 6) != 0 else od
         nz = (int(size[2]) + od2 - 1) // od2
-        per, rem = divmod(nz, world)
-        zb = rank * per + min(rank, rem)
-        zr = (zb, zb + per + (1 if rank < rem else 0))
+        zr = z_slab_range(nz, rank, world)
     res = eng.predict_volume(location, start, size, meanstd_x, meanstd_y, net=net, outdimsize=od, buffer=buf,
                              fetch_input=fetch_input, tile_z_range=zr)
     np_out = isinstance(location, np.ndarray) if as_numpy is None else as_numpy
