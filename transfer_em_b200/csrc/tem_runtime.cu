@@ -568,7 +568,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   tem_handle* h = new tem_handle();
   h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->keys_overridden = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
-  h->aux[0] = h->aux[1] = nullptr; for (int i = 0; i < 8; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
+  for (int i = 0; i < 4; ++i) h->aux[i] = nullptr; for (int i = 0; i < 12; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
   h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
   h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
   long long off = 0;
@@ -597,12 +597,12 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   if (cfg->train) {
     for (int i = 0; i < 6; ++i) if ((rc = alloc_gen_pass(h, h->gp[i], B, h->n))) return fail(rc);
     for (int i = 0; i < 4; ++i) if ((rc = alloc_disc_pass(h, h->dp[i], B, h->dm))) return fail(rc);
-    for (int sset = 0; sset < 2; ++sset) {
+    for (int sset = 0; sset < 4; ++sset) {
       for (int i = 0; i < 11; ++i) if ((rc = alloc_tensor(h, h->gdP[sset][i], DT_BF16, B, d[i], h->nets[0].L[i].cout))) return fail(rc);
       for (int i = 0; i < 8; ++i) if ((rc = alloc_tensor(h, h->ddP[sset][i], DT_BF16, B, dd[i] > 0 ? dd[i] : 1, h->nets[2].L[i].cout))) return fail(rc);
     }
-    for (int i = 0; i < 2; ++i) if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) { tem_set_error("stream create failed"); return fail(TEM_ERR_CUDA); }
-    for (int i = 0; i < 8; ++i) if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { tem_set_error("event create failed"); return fail(TEM_ERR_CUDA); }
+    for (int i = 0; i < 4; ++i) if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) { tem_set_error("stream create failed"); return fail(TEM_ERR_CUDA); }
+    for (int i = 0; i < 12; ++i) if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { tem_set_error("event create failed"); return fail(TEM_ERR_CUDA); }
     long long osz = (long long)B * h->outdim * h->outdim * (h->nd == 3 ? h->outdim : 1);
     for (int i = 0; i < 6; ++i) if ((rc = dev_alloc(h, (void**)&h->dOut[i], osz * 4))) return fail(rc);
     long long lsz = (long long)B * h->dl * h->dl * (h->nd == 3 ? h->dl : 1);
@@ -624,8 +624,8 @@ extern "C" int tem_destroy(tem_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  for (int i = 0; i < 2; ++i) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
-  for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 4; ++i) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+  for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);   // h_tile_index lives in the same allocation
   delete h;
@@ -820,20 +820,22 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   TEM_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)h->arena_elems * 4, st));
   const int G = TEM_NET_G, F = TEM_NET_F, DX = TEM_NET_DX, DY = TEM_NET_DY;
   GenPass* gp = h->gp; DiscPass* dp = h->dp;
-  // Independent passes run on two internal streams (A: G(real_x) -> F(fake_y) ..., B: F(real_y) -> G(fake_x) ...): most
+  // Independent passes run on four internal streams (A: G(real_x) -> F(fake_y), B: F(real_y) -> G(fake_x), C/D: identity
+  // passes and discriminators): most
   // kernels of this network are latency- rather than bandwidth-bound at wf=8, so overlapping two passes fills the SMs.
   // The first step of a handle (cold packed-weight cache), profiled steps and TEM_NO_OVERLAP=1 run on one stream.
   static const bool no_overlap = getenv("TEM_NO_OVERLAP") != nullptr;
   static const char* lim_s = getenv("TEM_DEBUG_GEN_BWD");
   const bool overlap = h->overlap_ready && !h->prof.on && !no_overlap && !lim_s;
-  cudaStream_t sA = overlap ? h->aux[0] : st, sB = overlap ? h->aux[1] : st;
-  const int setB = overlap ? 1 : 0;
+  cudaStream_t sA = overlap ? h->aux[0] : st, sB = overlap ? h->aux[1] : st, sC = overlap ? h->aux[2] : st, sD = overlap ? h->aux[3] : st;
+  cudaStream_t ss[4] = {sA, sB, sC, sD};
+  const int setB = overlap ? 1 : 0, setC = overlap ? 2 : 0, setD = overlap ? 3 : 0;
   if (overlap) {
-    // packed weight images are shared by both streams: refresh all of them before the fork
+    // packed weight images are shared by all streams: refresh all of them before the fork
     for (auto& kv : h->packed)
       if (kv.second.version != h->params_version) { TEM_CUDA(tc_pack_weights(kv.second.args, kv.second.buf, st)); kv.second.version = h->params_version; }
     TEM_CUDA(cudaEventRecord(h->ev[0], st));
-    TEM_CUDA(cudaStreamWaitEvent(sA, h->ev[0], 0)); TEM_CUDA(cudaStreamWaitEvent(sB, h->ev[0], 0));
+    for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   }
   // ---- forward (pass ids: 0 fake_y, 1 cycled_x, 2 fake_x, 3 cycled_y, 4 same_x, 5 same_y)
   InputRef fy, fx;                                                                     // ZeroPadding3D(buffer): :161,:170
@@ -845,17 +847,16 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   TEM_CHECK(make_input(h, gp[2].a[11].p, DT_F32, od, 0, nullptr, fxd));
   TEM_CHECK(gen_forward(h, G, gp[0], rx, B, n, keys + 0, sA));                         // cgan.py:152
   TEM_CHECK(gen_forward(h, F, gp[2], ry, B, n, keys + 4, sB));                         // :167
+  TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, sC));                         // :177
+  TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, sD));                        // :181
   TEM_CHECK(gen_forward(h, F, gp[1], fy, B, n, keys + 2, sA));                         // :162
   TEM_CHECK(gen_forward(h, G, gp[3], fx, B, n, keys + 6, sB));                         // :171
-  TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, sA));                         // :177
-  TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, sB));                        // :181
-  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sA));                               // :185
-  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sB));                               // :186
+  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sC));                               // :185
+  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sD));                               // :186
   TEM_CHECK(disc_forward(h, DX, dp[2], fxd, B, od, sB));                               // :188 (fake_x lives on stream B)
   TEM_CHECK(disc_forward(h, DY, dp[3], fyd, B, od, sA));                               // :189 (fake_y lives on stream A)
   if (overlap) {
-    TEM_CUDA(cudaEventRecord(h->ev[1], sA)); TEM_CUDA(cudaEventRecord(h->ev[2], sB));
-    TEM_CUDA(cudaStreamWaitEvent(st, h->ev[1], 0)); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[2], 0));
+    for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[1 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[1 + i], 0)); }
   }
   // ---- losses (accumulators live behind the gradient arena so one all-reduce covers both)
   float* LS = h->loss_dev;
@@ -878,16 +879,17 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   TEM_CHECK(pair_loss(h, rx, (const float*)gp[4].a[11].p, B, 0, s_id, LS + 8, h->dOut[4], st));      // identity f :200
   TEM_CHECK(pair_loss(h, ry, (const float*)gp[5].a[11].p, B, 0, s_id, LS + 7, h->dOut[5], st));      // identity g :199
   if (overlap) {
-    TEM_CUDA(cudaEventRecord(h->ev[3], st));
-    TEM_CUDA(cudaStreamWaitEvent(sA, h->ev[3], 0)); TEM_CUDA(cudaStreamWaitEvent(sB, h->ev[3], 0));
+    TEM_CUDA(cudaEventRecord(h->ev[5], st));
+    for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[5], 0));
   }
-  // ---- backward.  Stream A owns fake_y's gradient (dOut[0]), stream B fake_x's (dOut[2]).
+  // ---- backward.  Stream A owns fake_y's gradient (dOut[0]), stream B fake_x's (dOut[2]); C and D take the
+  // discriminators' own gradients and the identity passes.
   TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[0], false, h->dOut[0], sA, 0));      // d gen_g / d fake_y
   TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[1], false, h->dOut[2], sB, setB));   // d gen_f / d fake_x
-  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sA, 0));          // disc_y wrt D_y   :214
-  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sB, setB));       // disc_x wrt D_x   :212
-  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sA, 0));
-  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sB, setB));
+  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sC, setC));       // disc_y wrt D_y   :214
+  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sD, setD));       // disc_x wrt D_x   :212
+  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sC, setC));
+  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sD, setD));
   {
     // debug knob: TEM_DEBUG_GEN_BWD=k runs only the first k generator backward passes (scratch then holds pass k)
     const int lim = lim_s ? atoi(lim_s) : 6;
@@ -895,12 +897,11 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
     if (lim > 1) TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], sB, setB));      // cycled_y -> G, and into fake_x
     if (lim > 2) TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, sA, 0));
     if (lim > 3) TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, sB, setB));
-    if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, sA, 0));
-    if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, sB, setB));
+    if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, sC, setC));
+    if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, sD, setD));
   }
   if (overlap) {
-    TEM_CUDA(cudaEventRecord(h->ev[4], sA)); TEM_CUDA(cudaEventRecord(h->ev[5], sB));
-    TEM_CUDA(cudaStreamWaitEvent(st, h->ev[4], 0)); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[5], 0));
+    for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[6 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[6 + i], 0)); }
   }
   h->overlap_ready = !h->packed.empty() || !h->cfg.use_tensor_cores;
   return TEM_OK;
@@ -965,7 +966,7 @@ extern "C" int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* co
 extern "C" int tem_debug_backward_scratch(tem_handle* h, int is_gen, int layer, float* dst, int64_t* count, void* stream) {
   if (!h || !count || !h->cfg.train) ARG_FAIL("bad arguments");
   if (layer < 0 || layer >= (is_gen ? 11 : 8)) ARG_FAIL("bad layer");
-  Tensor t = is_gen ? h->gdP[h->overlap_ready ? 1 : 0][layer] : h->ddP[h->overlap_ready ? 1 : 0][layer];
+  Tensor t = is_gen ? h->gdP[h->overlap_ready ? 3 : 0][layer] : h->ddP[h->overlap_ready ? 1 : 0][layer];
   const int B = is_gen ? h->gp[5].B : h->dp[2].B;
   if (is_gen) { int d[12]; gen_dims(h->n, d); spatial(h, d[layer], t.d); }
   else { int d[9]; disc_dims(h->dm, h->nd, d); spatial(h, d[layer] > 0 ? d[layer] : 1, t.d); }

@@ -79,8 +79,8 @@ struct tem_handle {
   // workspaces
   GenPass gp[7];               // 0..5 train passes, 6 inference / API pass
   DiscPass dp[5];              // 0..3 train passes (DxR, DyR, DxF, DyF), 4 API pass
-  Tensor gdP[2][11];           // generator backward scratch (bf16): one set per internal stream
-  Tensor ddP[2][8];            // discriminator backward scratch
+  Tensor gdP[4][11];           // generator backward scratch (bf16): one set per internal stream
+  Tensor ddP[4][8];            // discriminator backward scratch
   float* dOut[6];              // gradient w.r.t. each generator pass output (fp32)
   float* dlog[6];              // logit gradients: gen_y, gen_x, dyr, dyf, dxr, dxf
   int* tile_origins; int* tile_index;   // device, maxB*3 each
@@ -95,9 +95,9 @@ struct tem_handle {
   struct Packed { bf16* buf; size_t bytes; uint64_t version; ConvArgs args; };
   std::map<std::tuple<const float*, int, int>, Packed> packed;
   uint64_t params_version;
-  // two internal streams overlap the independent passes of a train step (G(real_x) || F(real_y), ...)
-  cudaStream_t aux[2];
-  cudaEvent_t ev[8];
+  // four internal streams overlap the independent passes of a train step (G(real_x) || F(real_y), ...)
+  cudaStream_t aux[4];
+  cudaEvent_t ev[12];
   bool overlap_ready;
 };
 
