@@ -349,3 +349,12 @@ def test_single_channel_conv_fast_paths():
     dx = conv_dgrad(torch.tensor(dy).to(DEV), _cuda(w1, torch.float32), d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
     dref = naive.conv_dgrad(dy.astype(np.float64), w1, 1, x.shape) * naive.lrelu_grad_from_output(act, 0.3)
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
+
+
+def test_tma_wgrad_variant_in_subprocess():
+    """The opt-in TMA-ring weight-gradient kernel (TEM_WGRAD_TMA=1) must agree with the oracle too."""
+    import os, subprocess, sys
+    env = dict(os.environ, TEM_WGRAD_TMA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "tensor_core_wgrad", "-x"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kWarpsC * 32) conv_mma_kernel(const CmArgs a) 
   const int hvox = a.HZ * a.HY * a.HX;
   const int npad = NBT * 8;
 
-  constexpr int R = 2;                                    // rows of 16 positions per warp
+  constexpr int R = 4;                                    // rows of 16 positions per warp
   const int nrows = a.TZ * a.TY;
   float acc[R][NBT][4];
 #pragma unroll
@@ -251,12 +251,12 @@ cudaError_t launch_conv_mma(const ConvArgs& c, cudaStream_t st) {
     wb = ((ksteps * a.NB * 8 * 32) + 127) & ~127;
     return sb + wb;
   };
-  int TZ = Q[0] >= 2 ? 2 : 1, TY = Q[1] >= 8 ? 8 : (Q[1] >= 4 ? 4 : (Q[1] >= 2 ? 2 : 1));
+  int TZ = Q[0] >= 4 ? 4 : (Q[0] >= 2 ? 2 : 1), TY = Q[1] >= 8 ? 8 : (Q[1] >= 4 ? 4 : (Q[1] >= 2 ? 2 : 1));
   int hz, hy, hx, sb, wb;
-  while (sizes(TZ, TY, hz, hy, hx, sb, wb) > 160 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ = 1; else TY >>= 1; }
+  while (sizes(TZ, TY, hz, hy, hx, sb, wb) > 100 * 1024 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
   // small problems: prefer more CTAs over taller tiles
   auto ntiles = [&](int tz, int ty) { return (long long)c.B * ((Q[0] + tz - 1) / tz) * ((Q[1] + ty - 1) / ty) * ((Q[2] + TXC - 1) / TXC); };
-  while (ntiles(TZ, TY) < 148 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ = 1; else TY >>= 1; }
+  while (ntiles(TZ, TY) * ((c.form == 1) ? c.stride[0] * c.stride[1] * c.stride[2] : 1) < 2 * 148 && (TZ > 1 || TY > 1)) { if (TZ > 1) TZ >>= 1; else TY >>= 1; }
   const int smem = sizes(TZ, TY, hz, hy, hx, sb, wb);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   a.TZ = TZ; a.TY = TY; a.HZ = hz; a.HY = hy; a.HX = hx; a.s_bytes = sb; a.w_bytes = wb;

@@ -119,6 +119,10 @@ cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st);
 bool wgrad_mma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);
 
+// wgrad_tma.cu: TMA-staged, z-marching version of the tensor-core weight gradient
+bool wgrad_tma_supported(const WgradArgs& a);
+cudaError_t launch_wgrad_tma(const WgradArgs& a, cudaStream_t st);
+
 // wgrad_c1.cu: weight gradient of the single-channel first / last layers
 bool wgrad_c1_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_c1(const WgradArgs& a, cudaStream_t st);

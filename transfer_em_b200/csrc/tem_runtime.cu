@@ -314,7 +314,10 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
     ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
     static const bool no_mma = getenv("TEM_NO_WGRAD_MMA") != nullptr, no_c1 = getenv("TEM_NO_WGRAD_C1") != nullptr;   // debug knobs
-    if (h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
+    // TMA-ring variant (wgrad_tma.cu): measured slower than the cp.async tiles at wf=8 (profiles/README.md), opt-in
+    static const bool use_tma = getenv("TEM_WGRAD_TMA") != nullptr;
+    if (h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) TEM_CUDA(launch_wgrad_tma(a, st));
+    else if (h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
     else if (h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) TEM_CUDA(launch_wgrad_c1(a, st));
     else TEM_CUDA(launch_wgrad_direct(a, st));
   }
