@@ -1,0 +1,313 @@
+// tcgen05 implicit-GEMM 3x3x3 stride-1 convolution, second generation: the three kz taps share one MMA.
+//
+// conv_tc.cu issues, per OUTPUT z-slice, 27*Cin/16 MMAs of shape M128 x N(Cout) x K16; with Cout = 8..32 every one of
+// them re-reads a 4 KB A tile from shared memory for 8-16 cycles of math, and ncu shows the kernel pinned at the
+// shared-memory A-read rate (profiles/README.md).  Here the MMAs are issued per INPUT z-slice instead: an input slice s
+// contributes to the output slices s, s-1, s-2 through the taps kz = 0, 1, 2, so one MMA with
+// N' = 3*CP columns (B = [W(kz=0) | W(kz=1) | W(kz=2)]) accumulates all three at once into three ADJACENT column
+// groups of a TMEM-resident accumulator strip: output slice zo lives at column (ZCAP + 1 - zo) * CP, hence slices
+// s, s-1, s-2 are consecutive.  One third of the MMAs and of the A-operand traffic; every input slice is consumed by
+// exactly one MMA batch (the ring slot is released at once); accumulators of a whole z-chunk stay in TMEM
+// (<= 512 columns), are zeroed once with tcgen05.st and drained slice by slice by the epilogue warps while later
+// slices are still being accumulated.  Everything else (TMA halo planes, descriptors, fused epilogues) is conv_tc.cu's.
+#include <cuda.h>
+#include <string.h>
+#include "tem_kernels.cuh"
+#include "ptx_sm100.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int TX = 8, TY = 16, HX = TX + 2, HY = TY + 2;
+constexpr int PLANE_BYTES = HY * HX * 16;
+constexpr int PLANE_STRIDE = 2944;
+constexpr int RING3 = 4;
+constexpr int kTcThreads = 192;
+constexpr int kMaxChunk = 64;
+
+struct Tc3Args {
+  int B, L[3];                 // conv output extent (z,y,x)
+  int planes0, planes1;        // 8-channel planes taken from map0 / map1
+  int shift0[3], shift1[3];    // tensor coordinate = conv-input coordinate + shift (z,y,x)
+  int spd;                     // k-steps (K=16 MMAs) per dz
+  int cin8;                    // 1 when Cin == 8 (tap-pair k-steps)
+  const bf16* wpacked; int wbytes;
+  int ntx, nty, nzc, zc, zcap, tmem_cols;
+  bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
+  int Cout;
+  float slope;
+  const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
+  uint32_t drop_key;
+  int accumulate;
+};
+
+
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
+  constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[RING3], empty_bar[RING3], w_bar, tzero_bar, tfull_bar[kMaxChunk];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int planes = a.planes0 + a.planes1;
+  const uint32_t wbytes_pad = (uint32_t)((a.wbytes + 1023) & ~1023);
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + wbytes_pad;
+  const uint32_t slot_bytes = (uint32_t)planes * PLANE_STRIDE;
+
+  // work item
+  int w = blockIdx.x;
+  const int zc_i = w % a.nzc; w /= a.nzc;
+  const int tx_i = w % a.ntx; w /= a.ntx;
+  const int ty_i = w % a.nty; w /= a.nty;
+  const int b = w;
+  const int x0 = tx_i * TX, y0 = ty_i * TY, z0 = zc_i * a.zc;
+  const int nz = min(a.zc, a.L[0] - z0);
+  const int nslices = nz + 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING3; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&w_bar, 1); mbar_init(&tzero_bar, 128);
+    for (int i = 0; i < nz; ++i) mbar_init(&tfull_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
+      bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
+      int slot = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s) {
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * PLANE_BYTES);
+        uint8_t* dst = ring + (size_t)slot * slot_bytes;
+        for (int p = 0; p < a.planes0; ++p)
+          tma_load_5d(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], p * 8, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
+        for (int p = 0; p < a.planes1; ++p)
+          tma_load_5d(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], p * 8, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
+        if (++slot == RING3) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(&w_bar, 0);
+      mbar_wait(&tzero_bar, 0);                     // accumulator strip has been zeroed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t rbase = smem_u32(ring);
+      int slot = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s) {
+        mbar_wait(&full_bar[slot], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // columns of output slices s (kz=0), s-1 (kz=1), s-2 (kz=2) are adjacent
+        const uint32_t d_tmem = tmem_base + (uint32_t)((a.zcap + 1 - s) * CP);
+        const uint32_t sbase = rbase + (uint32_t)slot * slot_bytes;
+        int step = 0;
+        if (a.cin8) {
+#pragma unroll
+          for (int p = 0; p < 5; ++p) {
+            const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
+            const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3)) * 16u;
+            const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3)) * 16u;
+            const uint32_t lbo = (t1 == t0) ? 0u : (o1 - o0);
+            umma_bf16(d_tmem, umma_desc(sbase + o0, lbo, HX * 16), umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, 1u);
+            ++step;
+          }
+        } else {
+          const int kcs = planes >> 1;
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t o = (uint32_t)((t / 3) * HX + (t % 3)) * 16u;
+            for (int kc = 0; kc < kcs; ++kc) {
+              umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(2 * kc) * PLANE_STRIDE + o, PLANE_STRIDE, HX * 16),
+                        umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, 1u);
+              ++step;
+            }
+          }
+        }
+        umma_commit(&empty_bar[slot]);                       // the input slice is consumed by this batch only
+        if (s >= 2) umma_commit(&tfull_bar[s - 2]);          // output slice s-2 has received its three kz parts
+        if (++slot == RING3) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int oy = y0 + yl, ox = x0 + xl;
+    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // zero the accumulator strip (this warp's 32 lanes, all allocated columns)
+    for (int c = 0; c < a.tmem_cols; c += 8) tmem_st8_zero(lane_base + (uint32_t)c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&tzero_bar);
+    for (int zo = 0; zo < nz; ++zo) {
+      mbar_wait(&tfull_bar[zo], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[CP];
+      const uint32_t taddr = lane_base + (uint32_t)((a.zcap + 1 - zo) * CP);
+#pragma unroll
+      for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + c, r + c);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!inside) continue;
+      const int oz = z0 + zo;
+      float v[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) v[c] = __uint_as_float(r[c]);
+      if (a.ref) {
+        const long long ro = ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+#pragma unroll
+        for (int c = 0; c < CP; c += 8) {
+          if (c < a.Cout) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(a.ref + ro + c), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
+          }
+        }
+      }
+      if (a.drop_key) {
+        const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
+      }
+      bf16* op = a.out + ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
+#pragma unroll
+      for (int c = 0; c < CP; c += 8) {
+        if (c < a.Cout) {
+          float o[8];
+          if (a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
+          else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            o[u] += v[c + u];
+            if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
+          }
+          uint4 pk;
+          pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(op + c) = pk;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+  }
+}
+
+// bf16 UMMA B image [step][k-half][n-group][8 rows][8 elems] with n = (kz, co): N' = 3*CP columns (32 when CP == 8)
+struct Pack3Args {
+  const float* w; long long ws_tap, ws_in, ws_out;
+  int flip, cin, cols, cp, np, spd, cin8;
+  bf16* dst; int total;
+};
+__global__ void pack_weights3_kernel(const Pack3Args a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  int t = i;
+  const int e = t & 7; t >>= 3;
+  const int r = t & 7; t >>= 3;
+  const int ng = a.np >> 3;
+  const int g = t % ng; t /= ng;
+  const int j = t & 1; t >>= 1;
+  const int s = t;
+  int tap9, ci;
+  if (a.cin8) { tap9 = 2 * s + j; ci = e; }
+  else { const int kcs = a.cin >> 4; tap9 = s / kcs; ci = (2 * (s % kcs) + j) * 8 + e; }
+  const int n = g * 8 + r;
+  const int dz = n / a.cp, co = n % a.cp;
+  float v = 0.f;
+  if (tap9 < 9 && dz < 3 && co < a.cols) {
+    int tap = dz * 9 + tap9;
+    if (a.flip) tap = 26 - tap;
+    v = a.w[tap * a.ws_tap + (long long)ci * a.ws_in + (long long)co * a.ws_out];
+  }
+  a.dst[i] = __float2bfloat16_rn(v);
+}
+
+int cp_of(int cout) { return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32); }
+int np_of(int cp) { return cp == 8 ? 32 : 3 * cp; }
+
+}  // namespace
+
+size_t tc3_packed_bytes(int cin, int cout) {
+  const int spd = (cin == 8) ? 5 : 9 * (cin / 16);
+  return (size_t)spd * np_of(cp_of(cout)) * 32;
+}
+
+cudaError_t tc3_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  Pack3Args p;
+  const int cin = a.C0 + a.C1;
+  p.w = a.w; p.ws_tap = a.ws_tap; p.ws_in = a.ws_in; p.ws_out = a.ws_out;
+  p.flip = (a.form == 1) ? 1 : 0;
+  p.cin = cin; p.cols = a.Cout; p.cp = cp_of(a.Cout); p.np = np_of(p.cp);
+  p.cin8 = cin == 8; p.spd = p.cin8 ? 5 : 9 * (cin / 16);
+  p.dst = dst; p.total = (int)(tc3_packed_bytes(cin, a.Cout) / 2);
+  pack_weights3_kernel<<<(p.total + 255) / 256, 256, 0, st>>>(p); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t st) {
+  Tc3Args t; memset(&t, 0, sizeof(t));
+  const int cin = a.C0 + a.C1;
+  t.B = a.B; for (int i = 0; i < 3; ++i) t.L[i] = a.L[i];
+  t.planes0 = a.C0 / 8; t.planes1 = a.C1 / 8;
+  const int pad = (a.form == 1) ? 2 : 0;
+  for (int i = 0; i < 3; ++i) { t.shift0[i] = a.s0.shift[i] - pad; t.shift1[i] = a.s1.shift[i] - pad; }
+  t.cin8 = cin == 8; t.spd = t.cin8 ? 5 : 9 * (cin / 16);
+  t.wpacked = wpacked; t.wbytes = (int)tc3_packed_bytes(cin, a.Cout);
+  t.ntx = (a.L[2] + TX - 1) / TX; t.nty = (a.L[1] + TY - 1) / TY;
+  const int cp = cp_of(a.Cout);
+  // accumulator strip: (zcap + 5) column groups of CP columns; 256 columns keep two CTAs per SM when that leaves a
+  // useful chunk, otherwise the whole TMEM (one CTA per SM)
+  t.tmem_cols = (cp == 8) ? 256 : 512;
+  t.zcap = t.tmem_cols / cp - 5;
+  if (t.zcap > kMaxChunk) t.zcap = kMaxChunk;
+  const long long cols = (long long)a.B * t.ntx * t.nty;
+  int nzc = (a.L[0] + t.zcap - 1) / t.zcap;
+  while (cols * nzc < 2 * 148 && (a.L[0] + nzc) / (nzc + 1) >= 6) ++nzc;
+  t.zc = (a.L[0] + nzc - 1) / nzc; t.nzc = (a.L[0] + t.zc - 1) / t.zc;
+  t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
+  for (int i = 0; i < 3; ++i) { t.out_off[i] = a.out_off[i]; t.ref_off[i] = a.ref_off[i]; }
+  t.Cout = a.Cout; t.slope = a.slope;
+  t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
+  t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  CUtensorMap m0, m1;
+  if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
+  if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
+  else m1 = m0;
+  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)RING3 * (cin / 8) * PLANE_STRIDE + 1024;
+  const unsigned grid = (unsigned)(cols * t.nzc);
+  static bool attr[3] = {false, false, false};
+#define LAUNCH_TC3(CPV, IDX)                                                                                            \
+  {                                                                                                                     \
+    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv3_tc3_kernel<CPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
+    conv3_tc3_kernel<CPV><<<grid, kTcThreads, smem, st>>>(m0, m1, t);                                                   \
+  }
+  if (cp == 8) LAUNCH_TC3(8, 0) else if (cp == 16) LAUNCH_TC3(16, 1) else LAUNCH_TC3(32, 2)
+#undef LAUNCH_TC3
+  ++g_tem_launches;
+  return cudaGetLastError();
+}

@@ -107,6 +107,11 @@ size_t tc_packed_bytes(int cin, int cout);
 cudaError_t tc_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 
+// conv_tc3.cu: second-generation tcgen05 kernel (three kz taps per MMA, TMEM-resident accumulator strip)
+size_t tc3_packed_bytes(int cin, int cout);
+cudaError_t tc3_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
+cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
+
 // conv_mma.cu: mma.sync convolution for stride-2 / transposed / 1x1 layers with channel counts that are multiples of 8
 bool conv_mma_supported(const ConvArgs& a);
 cudaError_t launch_conv_mma(const ConvArgs& a, cudaStream_t st);

@@ -184,27 +184,28 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   for (int ax = 0; ax < 3; ++ax) if (a.L[ax] <= 0) return TEM_OK;
   static const bool no_tc = getenv("TEM_NO_CONV_TC") != nullptr;   // debug knob
   if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) {
-    const size_t bytes = tc_packed_bytes(a.C0 + a.C1, a.Cout);
+    static const bool gen1 = getenv("TEM_CONV_TC_GEN1") != nullptr;   // debug knob: first-generation kernel (one MMA batch per output slice)
+    const size_t bytes = gen1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout);
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
       TEM_CUDA(cudaMallocAsync((void**)&tmp, bytes, st));
-      TEM_CUDA(tc_pack_weights(a, tmp, st));
-      TEM_CUDA(launch_conv_tc(a, tmp, st));
+      if (gen1) { TEM_CUDA(tc_pack_weights(a, tmp, st)); TEM_CUDA(launch_conv_tc(a, tmp, st)); }
+      else { TEM_CUDA(tc3_pack_weights(a, tmp, st)); TEM_CUDA(launch_conv_tc3(a, tmp, st)); }
       TEM_CUDA(cudaFreeAsync(tmp, st));
       return TEM_OK;
     }
     auto key = std::make_tuple(a.w, a.form, a.Cout);
     auto it = h->packed.find(key);
     if (it == h->packed.end()) {
-      tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a;
+      tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a; p.gen1 = gen1;
       TEM_CHECK(dev_alloc(h, (void**)&p.buf, bytes));
       it = h->packed.emplace(key, p).first;
     }
     if (it->second.version != h->params_version) {
-      TEM_CUDA(tc_pack_weights(a, it->second.buf, st));
+      if (gen1) TEM_CUDA(tc_pack_weights(a, it->second.buf, st)); else TEM_CUDA(tc3_pack_weights(a, it->second.buf, st));
       it->second.version = h->params_version;
     }
-    TEM_CUDA(launch_conv_tc(a, it->second.buf, st));
+    if (gen1) TEM_CUDA(launch_conv_tc(a, it->second.buf, st)); else TEM_CUDA(launch_conv_tc3(a, it->second.buf, st));
     return TEM_OK;
   }
   static const bool no_c1 = getenv("TEM_NO_CONV_C1") != nullptr;     // debug knob
@@ -836,7 +837,10 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   if (overlap) {
     // packed weight images are shared by all streams: refresh all of them before the fork
     for (auto& kv : h->packed)
-      if (kv.second.version != h->params_version) { TEM_CUDA(tc_pack_weights(kv.second.args, kv.second.buf, st)); kv.second.version = h->params_version; }
+      if (kv.second.version != h->params_version) {
+        if (kv.second.gen1) TEM_CUDA(tc_pack_weights(kv.second.args, kv.second.buf, st)); else TEM_CUDA(tc3_pack_weights(kv.second.args, kv.second.buf, st));
+        kv.second.version = h->params_version;
+      }
     TEM_CUDA(cudaEventRecord(h->ev[0], st));
     for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   }
