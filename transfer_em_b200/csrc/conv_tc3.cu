@@ -12,6 +12,7 @@
 // slices are still being accumulated.  Everything else (TMA halo planes, descriptors, fused epilogues) is conv_tc.cu's.
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include "tem_kernels.cuh"
 #include "ptx_sm100.cuh"
 
@@ -157,7 +158,16 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     mbar_arrive(&tzero_bar);
+    const bool has_c8[4] = {0 < a.Cout, 8 < a.Cout, 16 < a.Cout, 24 < a.Cout};
     for (int zo = 0; zo < nz; ++zo) {
+      const int oz = z0 + zo;
+      // operands of the fused epilogue are fetched BEFORE waiting for the accumulator (hides the global-load latency)
+      uint4 refq[CP / 8];
+      if (a.ref && inside) {
+        const long long ro = ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+#pragma unroll
+        for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ro + c * 8));
+      }
       mbar_wait(&tfull_bar[zo], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[CP];
@@ -166,17 +176,15 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + c, r + c);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (!inside) continue;
-      const int oz = z0 + zo;
       float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) v[c] = __uint_as_float(r[c]);
       if (a.ref) {
-        const long long ro = ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
 #pragma unroll
         for (int c = 0; c < CP; c += 8) {
           if (c < a.Cout) {
             float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(a.ref + ro + c), f);
+            unpack8(refq[c / 8], f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
           }
@@ -282,7 +290,8 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   const int cp = cp_of(a.Cout);
   // accumulator strip: (zcap + 5) column groups of CP columns; 256 columns keep two CTAs per SM when that leaves a
   // useful chunk, otherwise the whole TMEM (one CTA per SM)
-  t.tmem_cols = (cp == 8) ? 256 : 512;
+  static const char* c16 = getenv("TEM_TC3_COLS16");
+  t.tmem_cols = (cp == 8) ? 256 : (cp == 16 ? (c16 ? atoi(c16) : 256) : 512);   // measured: 2 CTAs/SM beat a longer z-chunk at CP = 16
   t.zcap = t.tmem_cols / cp - 5;
   if (t.zcap > kMaxChunk) t.zcap = kMaxChunk;
   const long long cols = (long long)a.B * t.ntx * t.nty;
