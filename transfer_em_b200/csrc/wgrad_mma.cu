@@ -142,18 +142,16 @@ __global__ void __launch_bounds__(kWarps * 32, 2) wgrad_mma_kernel(const WgArgs 
     for (int row = rpart; row < a.TZ * a.TY; row += a.rsplit) {
       const int pz = row >> a.ty_sh, py = row & (a.TY - 1);
       const int rowbase = (pz * a.stride[0] * a.HY + py * a.stride[1]) * a.HX;
-      uint32_t b0 = 0, b1 = 0; int bcur = -1;
+      // branch-free over all kTPW slots (dead slots re-use tile 0's addresses and are discarded at the end): the
+      // compiler can issue the 16 ldmatrix pairs back to back instead of serialising ldmatrix -> mma latencies
+      uint32_t af[kTPW][4], bfr[kTPW][2];
 #pragma unroll
       for (int i = 0; i < kTPW; ++i) {
-        if (tile0 + i >= tile_end) continue;        // warp-uniform
-        if (nblk[i] != bcur) {
-          bcur = nblk[i];
-          ldsm_x2_t(pbuf + (uint32_t)(bcur * tvox + row * TXW + b_v) * 16u, b0, b1);
-        }
-        uint32_t a0, a1, a2, a3;
-        ldsm_x4_t(sbuf + (uint32_t)(rowbase + aoff[i]) * 16u, a0, a1, a2, a3);
-        mma_bf16(acc[i], a0, a1, a2, a3, b0, b1);
+        ldsm_x2_t(pbuf + (uint32_t)(nblk[i] * tvox + row * TXW + b_v) * 16u, bfr[i][0], bfr[i][1]);
+        ldsm_x4_t(sbuf + (uint32_t)(rowbase + aoff[i]) * 16u, af[i][0], af[i][1], af[i][2], af[i][3]);
       }
+#pragma unroll
+      for (int i = 0; i < kTPW; ++i) mma_bf16(acc[i], af[i][0], af[i][1], af[i][2], af[i][3], bfr[i][0], bfr[i][1]);
     }
     __syncthreads();
   }
