@@ -300,6 +300,14 @@ CM_CASES = [
     (4, 2, 16, 8, True, (6, 5, 20)),        # g9
     (1, 1, 32, 32, False, (1, 1, 1)),       # d7
     (3, 1, 16, 24, False, (5, 6, 17)),      # generic shape (NB = 3)
+    # tcgen05 stride-2 kernels (conv_tc_s2.cu): several (x,y) tiles with ragged edges, z chunks, odd extents
+    (4, 2, 8, 8, False, (22, 40, 38)),
+    (4, 2, 8, 16, False, (9, 36, 21)),
+    (4, 2, 16, 32, False, (14, 9, 40)),
+    (4, 2, 16, 8, True, (11, 19, 10)),
+    (4, 2, 32, 16, True, (4, 18, 9)),
+    (4, 2, 8, 8, True, (13, 5, 23)),
+    (4, 2, 16, 16, False, (32, 32, 32)),
 ]
 
 
@@ -323,6 +331,19 @@ def test_mma_conv_fwd_dgrad(k, s, cin, cout, tr, dims):
     dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
     assert rel_l2(dx, dref) < 4e-3
+
+
+def test_tcgen05_stride2_dropout_epilogue():
+    """Conv3DTranspose forward on the tcgen05 UP kernel with the fused Dropout(0.5) mask (models/utils.py:129-135)."""
+    key = 0x1234ABCD
+    r = np.random.default_rng(91)
+    x = bf16r(r.standard_normal((2, 5, 18, 9, 16)))
+    w = bf16r(r.standard_normal((4, 4, 4, 8, 16)) * 0.2)
+    d = make_desc(2, (5, 18, 9), 16, 8, 4, 2, True, 0.3, key, tc=1)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w, torch.float32), d).float().cpu().numpy()
+    pre = naive.convT_fwd(x, w)
+    ref = naive.lrelu(pre * O.dropout_keep_mask(key, pre.shape) * 2.0, 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
 
 
 def test_single_channel_conv_fast_paths():

@@ -1,0 +1,564 @@
+// tcgen05 implicit-GEMM kernels for the stride-2 layers of the reference graph (4x4x4 kernels):
+//   DOWN (form 0): out[o] = sum_k in[2o + k - pad] w[k]          strided downsample conv forward (models/utils.py:80)
+//                                                                and the data gradient of Conv3DTranspose (:129-130)
+//   UP   (form 1): out[j] = sum_{k = (j+pad) mod 2} in[(j+pad-k)/2] w[k]
+//                                                                Conv3DTranspose(4, 2, 'same') forward and the data
+//                                                                gradient of the strided conv
+//
+// Both are sums of 2x2x2-tap stride-1 correlations once the stride is folded into a parity split:
+//   DOWN: k - pad = 2m + r  ->  out[o] = sum_r sum_m in_r[o + m] w[2m + r + pad],  in_r = every second voxel of `in`.
+//         The de-interleaved halo tiles in_r are produced by TMA itself (tensor map with elementStrides = 2 along x and
+//         y; z is the slice coordinate), so a tap is again only a shifted UMMA descriptor start address.
+//         GEMM: M = 128 output voxels (16 y x 8 x of one output z-slice), N = Cout, K = 64 taps x Cin.
+//   UP:   j + pad = 2q + r  ->  out[2q + r - pad] = sum_{m'} in[q - 1 + m'] w[r + 2(1 - m')]: every output parity class
+//         r = (rz,ry,rx) is a 2x2x2 correlation over the SAME input window, so the eight classes become the N dimension:
+//         GEMM: M = 128 q-voxels, N = 8 classes x Cout, K = 8 taps x Cin; the epilogue scatters class r to voxel 2q+r-pad.
+// Everything else follows conv_tc.cu: one CTA marches along z over an (x,y) tile column, input slices are staged once
+// by TMA into an mbarrier ring (OOB zero-fill = padding), bf16 UMMA weight images are loaded once per CTA, accumulators
+// are double-buffered in TMEM, warp roles = TMA producer / MMA issuer / 4 epilogue warps with the fused
+// LeakyReLU / LeakyReLU' x dropout / accumulate epilogue.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "tem_kernels.cuh"
+#include "ptx_sm100.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int TX = 8, TY = 16;
+constexpr int SXV = TX + 1, SYR = TY + 1;          // sub-tile: 17 rows x 9 voxels of one 8-channel plane
+constexpr int SUB_BYTES = SYR * SXV * 16;          // 2448
+constexpr int SUB_STRIDE = 2560;                   // padded to a multiple of 128 B (TMA destination alignment)
+constexpr int ROW_B = SXV * 16;                    // 144: y-row pitch = stride between 8-row core-matrix groups
+constexpr int RING_MAX = 8;
+constexpr int kThreads = 192;
+constexpr int kThreadsUp = 320;              // UP: two epilogue warps per TMEM lane quadrant (one per output z parity)
+
+struct S2Args {
+  int B, L[3];                 // logical output extent (z,y,x)
+  int Q[3];                    // UP: q extents; DOWN: = L
+  int pad;                     // 0 or 1 (all axes)
+  int planes;                  // Cin / 8
+  int shift[3];                // tensor coordinate = conv-input coordinate + shift
+  int cin8;
+  const bf16* wpacked; int wbytes;
+  int ntx, nty, nzc, zc, ring;
+  bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
+  int Cout;
+  float slope;
+  const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
+  uint32_t drop_key;
+  int accumulate;
+};
+
+struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq: operands fetched ahead by the caller
+  __device__ static __forceinline__ long long ref_off(const S2Args& a, int b, int oz, int oy, int ox) {
+    return ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+  }
+  __device__ static __forceinline__ long long out_off(const S2Args& a, int b, int oz, int oy, int ox) {
+    return ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
+  }
+  __device__ static __forceinline__ void run(const S2Args& a, float* v, int c0, int b, int oz, int oy, int ox, const uint4& refq, const uint4& accq) {
+    if (a.ref) {
+      float f[8];
+      unpack8(refq, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
+    }
+    if (a.drop_key) {
+      const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout) + (uint32_t)c0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] *= 2.f * tem_keep(a.drop_key, di + u);
+    }
+    float o[8];
+    if (a.accumulate) unpack8(accq, o);
+    else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      o[u] += v[u];
+      if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
+    }
+    uint4 pk;
+    pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(a.out + out_off(a, b, oz, oy, ox) + c0) = pk;
+  }
+};
+
+__device__ __forceinline__ void decode_work(const S2Args& a, int& b, int& x0, int& y0, int& z0, int& nz) {
+  int w = blockIdx.x;
+  const int zc_i = w % a.nzc; w /= a.nzc;
+  const int tx_i = w % a.ntx; w /= a.ntx;
+  const int ty_i = w % a.nty; w /= a.nty;
+  b = w;
+  x0 = tx_i * TX; y0 = ty_i * TY; z0 = zc_i * a.zc;
+  nz = min(a.zc, a.Q[0] - z0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// UP: NP = 8 * CP accumulator columns per q-slice (class-major), two TMEM stages
+// ------------------------------------------------------------------------------------------------
+template <int CP>
+__global__ void __launch_bounds__(kThreadsUp)
+conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
+  constexpr int NP = 8 * CP;
+  constexpr uint32_t kTmemCols = 2 * NP;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[RING_MAX], empty_bar[RING_MAX], w_bar, tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int RING = a.ring;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int planes = a.planes;
+  const uint32_t wbytes_pad = (uint32_t)((a.wbytes + 1023) & ~1023);
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + wbytes_pad;
+  const uint32_t slot_bytes = (uint32_t)planes * SUB_STRIDE;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  int b, x0, y0, z0, nz; decode_work(a, b, x0, y0, z0, nz);
+  const int nslices = nz + 1;                      // input slices z0-1 .. z0+nz-1
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
+      bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
+      int slot = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s) {
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * SUB_BYTES);
+        uint8_t* dst = ring + (size_t)slot * slot_bytes;
+        for (int p = 0; p < planes; ++p)
+          tma_load_5d(dst + p * SUB_STRIDE, &map0, &full_bar[slot], p * 8, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 - 1 + s + a.shift[0], b);
+        if (++slot == RING) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(&w_bar, 0);
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t rbase = smem_u32(ring);
+      int waited = 0, wslot = 0, zslot = 0; uint32_t wph = 0;
+      const int kcs = planes >> 1;
+      for (int zo = 0; zo < nz; ++zo) {
+        while (waited < zo + 2) { mbar_wait(&full_bar[wslot], wph); ++waited; if (++wslot == RING) { wslot = 0; wph ^= 1u; } }
+        mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NP;
+        uint32_t acc = 0;
+        int step = 0;
+        for (int mz = 0; mz < 2; ++mz) {
+          int sl = zslot + mz; if (sl >= RING) sl -= RING;
+          const uint32_t sbase = rbase + (uint32_t)sl * slot_bytes;
+          for (int my = 0; my < 2; ++my) {
+            if (a.cin8) {          // one plane: the K=16 step covers the taps mx = 0, 1 (adjacent voxels)
+              umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(my * SXV) * 16u, 16u, ROW_B), umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, acc);
+              acc = 1; ++step;
+            } else {
+              for (int mx = 0; mx < 2; ++mx)
+                for (int kc = 0; kc < kcs; ++kc) {
+                  umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(2 * kc) * SUB_STRIDE + (uint32_t)(my * SXV + mx) * 16u, SUB_STRIDE, ROW_B),
+                            umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, acc);
+                  acc = 1; ++step;
+                }
+            }
+          }
+        }
+        umma_commit(&tfull_bar[zo & 1]);
+        umma_commit(&empty_bar[zslot]);      // input slice zo-1 is not used by later outputs
+        if (++zslot == RING) zslot = 0;
+      }
+    }
+  } else {
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int rz = (warp - 2) >> 2;                // output z parity handled by this warp
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int qy = y0 + yl, qx = x0 + xl;
+    constexpr int NCH = CP / 8;
+    constexpr bool kPrefetch = CP <= 16;           // operands of all four (ry,rx) classes are fetched before the accumulator wait
+    for (int zo = 0; zo < nz; ++zo) {
+      const int qz = z0 + zo;
+      const int oz = 2 * qz + rz - a.pad;
+      const bool zok = oz >= 0 && oz < a.L[0];
+      bool ok[4]; int oyv[4], oxv[4];
+      uint4 refq[kPrefetch ? 4 : 1][NCH], accq[kPrefetch ? 4 : 1][NCH];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        oyv[c4] = 2 * qy + (c4 >> 1) - a.pad; oxv[c4] = 2 * qx + (c4 & 1) - a.pad;
+        ok[c4] = zok && oyv[c4] >= 0 && oyv[c4] < a.L[1] && oxv[c4] >= 0 && oxv[c4] < a.L[2];
+        if (kPrefetch && ok[c4]) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c * 8 < a.Cout) {
+              if (a.ref) refq[c4][c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8));
+              if (a.accumulate) accq[c4][c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8);
+            }
+          }
+        }
+      }
+      mbar_wait(&tfull_bar[zo & 1], ((uint32_t)(zo >> 1)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo & 1) * NP + (uint32_t)(rz * 4 * CP);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        __syncwarp();
+        if (!kPrefetch && ok[c4]) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c * 8 < a.Cout) {
+              if (a.ref) refq[0][c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8));
+              if (a.accumulate) accq[0][c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8);
+            }
+          }
+        }
+        uint32_t r[CP];
+#pragma unroll
+        for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + (uint32_t)(c4 * CP + c), r + c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c4 == 3) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tempty_bar[zo & 1]);
+        }
+        if (ok[c4]) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c * 8 < a.Cout) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
+              Epi::run(a, v, c * 8, b, oz, oyv[c4], oxv[c4], refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c]);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DOWN: one ring slot = one input z-slice = 4 (ry,rx) de-interleaved sub-tiles x planes
+// ------------------------------------------------------------------------------------------------
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads)
+conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
+  constexpr uint32_t kTmemCols = (2 * NPAD < 32) ? 32 : 2 * NPAD;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[RING_MAX], empty_bar[RING_MAX], w_bar, tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int RING = a.ring;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int planes = a.planes;
+  const uint32_t wbytes_pad = (uint32_t)((a.wbytes + 1023) & ~1023);
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + wbytes_pad;
+  const uint32_t slot_bytes = (uint32_t)(4 * planes) * SUB_STRIDE;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  int b, x0, y0, z0, nz; decode_work(a, b, x0, y0, z0, nz);
+  const int nslices = 2 * nz + 2;                  // input slices 2*z0 - pad .. 2*(z0+nz-1) + 3 - pad
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
+      bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
+      int slot = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s) {
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(4 * planes) * SUB_BYTES);
+        uint8_t* dst = ring + (size_t)slot * slot_bytes;
+        const int zin = 2 * z0 - a.pad + s + a.shift[0];
+        for (int rr = 0; rr < 4; ++rr) {
+          const int ry = rr >> 1, rx = rr & 1;
+          // parity r of (k - pad): k = kb, kb + 2 with kb = (r + pad) & 1; first tap offset m_lo = (kb - pad - r) / 2
+          const int mly = (((ry + a.pad) & 1) - a.pad - ry) / 2, mlx = (((rx + a.pad) & 1) - a.pad - rx) / 2;
+          const int cy = 2 * (y0 + mly) + ry + a.shift[1], cx = 2 * (x0 + mlx) + rx + a.shift[2];
+          for (int p = 0; p < planes; ++p)
+            tma_load_5d(dst + (rr * planes + p) * SUB_STRIDE, &map0, &full_bar[slot], p * 8, cx, cy, zin, b);
+        }
+        if (++slot == RING) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(&w_bar, 0);
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t rbase = smem_u32(ring);
+      int waited = 0, wslot = 0, zslot = 0; uint32_t wph = 0;
+      const int kcs = planes >> 1;
+      for (int zo = 0; zo < nz; ++zo) {
+        while (waited < 2 * zo + 4) { mbar_wait(&full_bar[wslot], wph); ++waited; if (++wslot == RING) { wslot = 0; wph ^= 1u; } }
+        mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NPAD;
+        uint32_t acc = 0;
+        int step = 0;
+        for (int kz = 0; kz < 4; ++kz) {
+          int sl = zslot + kz; if (sl >= RING) sl -= RING;
+          const uint32_t sbase = rbase + (uint32_t)sl * slot_bytes;
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t tbase = sbase + (uint32_t)(rr * planes) * SUB_STRIDE;
+            for (int my = 0; my < 2; ++my) {
+              if (a.cin8) {
+                umma_bf16(d_tmem, umma_desc(tbase + (uint32_t)(my * SXV) * 16u, 16u, ROW_B), umma_desc(wbase + (uint32_t)step * (NPAD * 32), NPAD * 16, 128), idesc, acc);
+                acc = 1; ++step;
+              } else {
+                for (int mx = 0; mx < 2; ++mx)
+                  for (int kc = 0; kc < kcs; ++kc) {
+                    umma_bf16(d_tmem, umma_desc(tbase + (uint32_t)(2 * kc) * SUB_STRIDE + (uint32_t)(my * SXV + mx) * 16u, SUB_STRIDE, ROW_B),
+                              umma_desc(wbase + (uint32_t)step * (NPAD * 32), NPAD * 16, 128), idesc, acc);
+                    acc = 1; ++step;
+                  }
+              }
+            }
+          }
+        }
+        umma_commit(&tfull_bar[zo & 1]);
+        umma_commit(&empty_bar[zslot]);                          // input slices 2zo and 2zo+1 are done
+        int s1 = zslot + 1; if (s1 >= RING) s1 -= RING;
+        umma_commit(&empty_bar[s1]);
+        zslot += 2; if (zslot >= RING) zslot -= RING;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int oy = y0 + yl, ox = x0 + xl;
+    const bool inside = oy < a.L[1] && ox < a.L[2];
+    for (int zo = 0; zo < nz; ++zo) {
+      const int oz = z0 + zo;
+      uint4 refq[NPAD / 8], accq[NPAD / 8];
+      if (inside) {
+#pragma unroll
+        for (int c = 0; c < NPAD / 8; ++c) {
+          if (c * 8 < a.Cout) {
+            if (a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + c * 8));
+            if (a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + c * 8);
+          }
+        }
+      }
+      mbar_wait(&tfull_bar[zo & 1], ((uint32_t)(zo >> 1)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[NPAD];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo & 1) * NPAD;
+#pragma unroll
+      for (int c = 0; c < NPAD; c += 8) tmem_ld8(taddr + c, r + c);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty_bar[zo & 1]);
+      if (!inside) continue;
+#pragma unroll
+      for (int c = 0; c < NPAD / 8; ++c) {
+        if (c * 8 < a.Cout) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
+          Epi::run(a, v, c * 8, b, oz, oy, ox, refq[c], accq[c]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// bf16 UMMA B image [step][k-half][n-group][8 rows][8 elems]; the step order is the issue order of the kernels above
+struct PackS2Args {
+  const float* w; long long ws_tap, ws_in, ws_out;
+  int up, pad, cin, cols, cp, np, cin8;
+  bf16* dst; int total;
+};
+__global__ void pack_weights_s2_kernel(const PackS2Args a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  int t = i;
+  const int e = t & 7; t >>= 3;
+  const int r = t & 7; t >>= 3;
+  const int ng = a.np >> 3;
+  const int g = t % ng; t /= ng;
+  const int j = t & 1; t >>= 1;
+  int s = t;
+  const int n = g * 8 + r;
+  const int kcs = a.cin >> 4;
+  int mx, ci;
+  if (a.cin8) { mx = j; ci = e; }
+  else { const int kc = s % kcs; s /= kcs; mx = s & 1; s >>= 1; ci = (2 * kc + j) * 8 + e; }
+  const int my = s & 1; s >>= 1;
+  int kz, ky, kx, co;
+  if (a.up) {
+    const int mz = s & 1;
+    const int cls = n / a.cp; co = n % a.cp;
+    const int rz = cls >> 2, ry = (cls >> 1) & 1, rx = cls & 1;
+    kz = rz + 2 * (1 - mz); ky = ry + 2 * (1 - my); kx = rx + 2 * (1 - mx);
+  } else {
+    const int rr = s & 3; s >>= 2;
+    kz = s;
+    const int ry = rr >> 1, rx = rr & 1;
+    const int kby = (ry + a.pad) & 1, kbx = (rx + a.pad) & 1;      // k = kb + 2 m'
+    ky = kby + 2 * my; kx = kbx + 2 * mx;
+    co = n;
+  }
+  float v = 0.f;
+  if (co < a.cols) v = a.w[(long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)ci * a.ws_in + (long long)co * a.ws_out];
+  a.dst[i] = __float2bfloat16_rn(v);
+}
+
+int cp_of(int cout) { return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32); }
+int npad_of(int cout) { return cout <= 16 ? 16 : 32; }
+int steps_of(const ConvArgs& a) {
+  const int cin = a.C0;
+  const int per_yz = (cin == 8) ? 1 : 2 * (cin / 16);
+  return (a.form == 1) ? 4 * per_yz : 32 * per_yz;
+}
+int ring_of(const ConvArgs& a, size_t& smem_out) {
+  const int cin = a.C0;
+  const size_t wb = (tc_s2_packed_bytes(a) + 1023) & ~(size_t)1023;
+  const size_t slot = (size_t)(a.form == 1 ? 1 : 4) * (cin / 8) * SUB_STRIDE;
+  const int want = (a.form == 1) ? 6 : 8, least = (a.form == 1) ? 3 : 5;
+  int ring = want;
+  while (ring > least && wb + ring * slot + 1024 > 200 * 1024) --ring;
+  smem_out = wb + ring * slot + 1024;
+  return ring;
+}
+
+}  // namespace
+
+size_t tc_s2_packed_bytes(const ConvArgs& a) {
+  const int np = (a.form == 1) ? 8 * cp_of(a.Cout) : npad_of(a.Cout);
+  return (size_t)steps_of(a) * np * 32;
+}
+
+bool tc_s2_supported(const ConvArgs& a) {
+  for (int i = 0; i < 3; ++i) if (a.k[i] != 4 || a.stride[i] != 2 || a.conv_off[i]) return false;
+  if (!(a.pad[0] == a.pad[1] && a.pad[1] == a.pad[2] && (a.pad[0] == 0 || a.pad[0] == 1))) return false;
+  if (a.form != 0 && a.form != 1) return false;
+  if (a.s0.dtype != DT_BF16 || a.out_dtype != DT_BF16) return false;
+  if (a.s0.origins || a.use_lut || a.bias || a.C1) return false;
+  const int cin = a.C0;
+  if (!(cin == 8 || (cin % 16 == 0 && cin <= 64))) return false;
+  if (a.s0.C != cin || a.s0.coff != 0) return false;
+  if (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8) return false;
+  if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
+  size_t smem; ring_of(a, smem);
+  if (smem > 200 * 1024) return false;
+  return tem_get_encode() != nullptr;
+}
+
+cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  PackS2Args p;
+  p.w = a.w; p.ws_tap = a.ws_tap; p.ws_in = a.ws_in; p.ws_out = a.ws_out;
+  p.up = a.form == 1; p.pad = a.pad[0]; p.cin = a.C0; p.cols = a.Cout; p.cp = cp_of(a.Cout);
+  p.np = p.up ? 8 * p.cp : npad_of(a.Cout); p.cin8 = a.C0 == 8;
+  p.dst = dst; p.total = (int)(tc_s2_packed_bytes(a) / 2);
+  pack_weights_s2_kernel<<<(p.total + 255) / 256, 256, 0, st>>>(p); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
+static bool make_map_s2(CUtensorMap* m, const void* base, int B, int Z, int Y, int X, int C, int es) {
+  EncodeTiledFn enc = tem_get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)Z, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)X * C * 2, (cuuint64_t)Y * X * C * 2, (cuuint64_t)Z * Y * X * C * 2};
+  // with element strides the box spans count * stride tensor elements and TMA keeps every stride-th one
+  cuuint32_t box[5] = {8, (cuuint32_t)(SXV * es), (cuuint32_t)(SYR * es), 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st) {
+  S2Args t; memset(&t, 0, sizeof(t));
+  const int cin = a.C0;
+  const bool up = a.form == 1;
+  t.B = a.B; t.pad = a.pad[0];
+  for (int i = 0; i < 3; ++i) {
+    t.L[i] = a.L[i]; t.shift[i] = a.s0.shift[i];
+    t.Q[i] = up ? ((a.L[i] - 1 + t.pad) >> 1) + 1 : a.L[i];
+    t.out_off[i] = a.out_off[i]; t.ref_off[i] = a.ref_off[i];
+  }
+  t.planes = cin / 8; t.cin8 = cin == 8;
+  t.wpacked = wpacked; t.wbytes = (int)tc_s2_packed_bytes(a);
+  t.ntx = (t.Q[2] + TX - 1) / TX; t.nty = (t.Q[1] + TY - 1) / TY;
+  const long long cols = (long long)a.B * t.ntx * t.nty;
+  size_t smem; t.ring = ring_of(a, smem);
+  // z chunks: as many CTAs as are resident at once (one wave), chunks of at least two slices
+  const int tmem_cols = up ? 16 * cp_of(a.Cout) : 2 * npad_of(a.Cout);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm > 2048 / (up ? kThreadsUp : kThreads)) per_sm = 2048 / (up ? kThreadsUp : kThreads);
+  if (up && per_sm > 2) per_sm = 2;              // register file: 320 threads x ~96 registers
+  if (per_sm < 1) per_sm = 1;
+  int nzc = (int)((148LL * per_sm) / cols);
+  if (nzc < 1) nzc = 1;
+  if (nzc > (t.Q[0] + 1) / 2) nzc = (t.Q[0] + 1) / 2;
+  if (nzc < 1) nzc = 1;
+  t.zc = (t.Q[0] + nzc - 1) / nzc; t.nzc = (t.Q[0] + t.zc - 1) / t.zc;
+  t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
+  t.Cout = a.Cout; t.slope = a.slope;
+  t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
+  t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  CUtensorMap m0;
+  if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, up ? 1 : 2)) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)(cols * t.nzc);
+  static bool attr[5] = {false, false, false, false, false};
+#define LAUNCH_S2(KERNEL, IDX)                                                                                          \
+  {                                                                                                                     \
+    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
+    KERNEL<<<grid, up ? kThreadsUp : kThreads, smem, st>>>(m0, t);                                                                       \
+  }
+  if (up) {
+    const int cp = cp_of(a.Cout);
+    if (cp == 8) LAUNCH_S2(conv_up_tc_kernel<8>, 0) else if (cp == 16) LAUNCH_S2(conv_up_tc_kernel<16>, 1) else LAUNCH_S2(conv_up_tc_kernel<32>, 2)
+  } else {
+    if (npad_of(a.Cout) == 16) LAUNCH_S2(conv_down_tc_kernel<16>, 3) else LAUNCH_S2(conv_down_tc_kernel<32>, 4)
+  }
+#undef LAUNCH_S2
+  ++g_tem_launches;
+  return cudaGetLastError();
+}

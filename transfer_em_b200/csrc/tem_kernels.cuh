@@ -112,6 +112,12 @@ size_t tc3_packed_bytes(int cin, int cout);
 cudaError_t tc3_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 
+// conv_tc_s2.cu: tcgen05 kernels for the 4x4x4 stride-2 layers (strided conv / transposed conv, forward and data gradient)
+bool tc_s2_supported(const ConvArgs& a);
+size_t tc_s2_packed_bytes(const ConvArgs& a);
+cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
+cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
+
 // conv_mma.cu: mma.sync convolution for stride-2 / transposed / 1x1 layers with channel counts that are multiples of 8
 bool conv_mma_supported(const ConvArgs& a);
 cudaError_t launch_conv_mma(const ConvArgs& a, cudaStream_t st);

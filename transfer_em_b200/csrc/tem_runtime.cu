@@ -178,34 +178,53 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
   for (int i = 0; i < 3; ++i) a.out_off[i] = off ? off[i] : 0;
 }
 
+static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  return kind == 2 ? tc_s2_pack_weights(a, dst, st) : (kind == 1 ? tc_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st));
+}
+static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
+  return kind == 2 ? launch_conv_tc_s2(a, wp, st) : (kind == 1 ? launch_conv_tc(a, wp, st) : launch_conv_tc3(a, wp, st));
+}
+
 // conv dispatch: tcgen05 implicit GEMM when the shape allows, direct kernel otherwise
 static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   tem_handle* h = const_cast<tem_handle*>(hc);
   for (int ax = 0; ax < 3; ++ax) if (a.L[ax] <= 0) return TEM_OK;
   static const bool no_tc = getenv("TEM_NO_CONV_TC") != nullptr;   // debug knob
-  if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) {
-    static const bool gen1 = getenv("TEM_CONV_TC_GEN1") != nullptr;   // debug knob: first-generation kernel (one MMA batch per output slice)
-    const size_t bytes = gen1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout);
+  static const bool no_s2 = getenv("TEM_NO_CONV_TC_S2") != nullptr;   // debug knob: stride-2 layers on the mma.sync kernel
+  static const bool gen1 = getenv("TEM_CONV_TC_GEN1") != nullptr;   // debug knob: first-generation kernel (one MMA batch per output slice)
+  int kind = -1;                                                    // packed-weight tcgen05 kernels
+  if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) kind = gen1 ? 1 : 0;
+  else if (h->cfg.use_tensor_cores && !no_tc && !no_s2 && tc_s2_supported(a)) kind = 2;
+  if (kind >= 0) {
+    const size_t bytes = kind == 2 ? tc_s2_packed_bytes(a) : (kind == 1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout));
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
+      static bool pool_kept = false;       // keep freed blocks in the default pool across synchronisations
+      if (!pool_kept) {
+        int dev = 0; cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_kept = true;
+      }
       TEM_CUDA(cudaMallocAsync((void**)&tmp, bytes, st));
-      if (gen1) { TEM_CUDA(tc_pack_weights(a, tmp, st)); TEM_CUDA(launch_conv_tc(a, tmp, st)); }
-      else { TEM_CUDA(tc3_pack_weights(a, tmp, st)); TEM_CUDA(launch_conv_tc3(a, tmp, st)); }
+      TEM_CUDA(pack_tc_weights(kind, a, tmp, st));
+      TEM_CUDA(launch_tc_kind(kind, a, tmp, st));
       TEM_CUDA(cudaFreeAsync(tmp, st));
       return TEM_OK;
     }
     auto key = std::make_tuple(a.w, a.form, a.Cout);
     auto it = h->packed.find(key);
     if (it == h->packed.end()) {
-      tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a; p.gen1 = gen1;
+      tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a; p.kind = kind;
       TEM_CHECK(dev_alloc(h, (void**)&p.buf, bytes));
       it = h->packed.emplace(key, p).first;
     }
     if (it->second.version != h->params_version) {
-      if (gen1) TEM_CUDA(tc_pack_weights(a, it->second.buf, st)); else TEM_CUDA(tc3_pack_weights(a, it->second.buf, st));
+      TEM_CUDA(pack_tc_weights(kind, a, it->second.buf, st));
       it->second.version = h->params_version;
     }
-    if (gen1) TEM_CUDA(launch_conv_tc(a, it->second.buf, st)); else TEM_CUDA(launch_conv_tc3(a, it->second.buf, st));
+    TEM_CUDA(launch_tc_kind(kind, a, it->second.buf, st));
     return TEM_OK;
   }
   static const bool no_c1 = getenv("TEM_NO_CONV_C1") != nullptr;     // debug knob
@@ -838,7 +857,7 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
     // packed weight images are shared by all streams: refresh all of them before the fork
     for (auto& kv : h->packed)
       if (kv.second.version != h->params_version) {
-        if (kv.second.gen1) TEM_CUDA(tc_pack_weights(kv.second.args, kv.second.buf, st)); else TEM_CUDA(tc3_pack_weights(kv.second.args, kv.second.buf, st));
+        TEM_CUDA(pack_tc_weights(kv.second.kind, kv.second.args, kv.second.buf, st));
         kv.second.version = h->params_version;
       }
     TEM_CUDA(cudaEventRecord(h->ev[0], st));
