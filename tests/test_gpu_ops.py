@@ -243,6 +243,15 @@ WG_CASES = [
     (4, 2, 32, 16, True, (5, 6, 7)),
     (4, 2, 16, 8, True, (6, 5, 20)),
     (1, 1, 32, 32, False, (1, 1, 1)),
+    # tcgen05 weight gradient (wgrad_tc.cu): every (planes, rows) plan, ragged rows / runs, z chunks
+    (3, 1, 8, 8, False, (12, 23, 37)),
+    (3, 1, 8, 16, False, (9, 12, 20)),
+    (3, 1, 8, 32, False, (6, 9, 19)),
+    (3, 1, 16, 8, False, (7, 11, 18)),
+    (3, 1, 16, 32, False, (10, 10, 10)),
+    (3, 1, 32, 8, False, (6, 8, 35)),
+    (3, 1, 32, 32, False, (5, 7, 21)),
+    (3, 1, 16, 16, False, (26, 9, 50)),
 ]
 
 

@@ -32,6 +32,7 @@ constexpr int kTcThreads = 192;
 struct TcArgs {
   int B, L[3];                 // conv output extent (z,y,x)
   int planes0, planes1;        // 8-channel planes taken from map0 / map1
+  int merged0, merged1;        // map folds (channel, x): see tem_make_map_c8
   int shift0[3], shift1[3];    // tensor coordinate = conv-input coordinate + shift (z,y,x)
   int spd;                     // k-steps (K=16 MMAs) per dz
   int cin8;                    // 1 when Cin == 8 (tap-pair k-steps)
@@ -96,9 +97,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * PLANE_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         for (int p = 0; p < a.planes0; ++p)
-          tma_load_5d(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], p * 8, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
+          tma_load_plane(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], a.merged0, p, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
         for (int p = 0; p < a.planes1; ++p)
-          tma_load_5d(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], p * 8, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
+          tma_load_plane(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], a.merged1, p, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
         if (++slot == RING) { slot = 0; ph ^= 1u; }
       }
     }
@@ -312,9 +313,9 @@ cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t 
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   CUtensorMap m0, m1;
-  if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
-  if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
-  else m1 = m0;
+  if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
+  if (a.C1) { if (!tem_make_map_plane(&m1, &t.merged1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
+  else { m1 = m0; t.merged1 = t.merged0; }
   const int npad = a.Cout <= 16 ? 16 : 32;
   // ring depth 5..12 within ~16 KB: measured, occupancy (CTAs per SM) hides TMA latency better than a deeper ring
   int ring = (int)((16 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));

@@ -23,18 +23,19 @@ namespace {
 constexpr int TX = 8, TY = 16, HX = TX + 2, HY = TY + 2;
 constexpr int PLANE_BYTES = HY * HX * 16;
 constexpr int PLANE_STRIDE = 2944;
-constexpr int RING3 = 4;
+constexpr int RING3_MAX = 16;
 constexpr int kTcThreads = 192;
 constexpr int kMaxChunk = 64;
 
 struct Tc3Args {
   int B, L[3];                 // conv output extent (z,y,x)
   int planes0, planes1;        // 8-channel planes taken from map0 / map1
+  int merged0, merged1;        // map folds (channel, x): see tem_make_map_c8
   int shift0[3], shift1[3];    // tensor coordinate = conv-input coordinate + shift (z,y,x)
   int spd;                     // k-steps (K=16 MMAs) per dz
   int cin8;                    // 1 when Cin == 8 (tap-pair k-steps)
   const bf16* wpacked; int wbytes;
-  int ntx, nty, nzc, zc, zcap, tmem_cols;
+  int ntx, nty, nzc, zc, zcap, tmem_cols, ring;
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
   float slope;
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
   constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[RING3], empty_bar[RING3], w_bar, tzero_bar, tfull_bar[kMaxChunk];
+  __shared__ uint64_t full_bar[RING3_MAX], empty_bar[RING3_MAX], w_bar, tzero_bar, tfull_bar[kMaxChunk];
+  const int RING3 = a.ring;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,51 +100,63 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * PLANE_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         for (int p = 0; p < a.planes0; ++p)
-          tma_load_5d(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], p * 8, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
+          tma_load_plane(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], a.merged0, p, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
         for (int p = 0; p < a.planes1; ++p)
-          tma_load_5d(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], p * 8, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
+          tma_load_plane(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], a.merged1, p, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
         if (++slot == RING3) { slot = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the issue loop convergently, so descriptors and barrier addresses stay in uniform registers;
+    // one elected lane issues the MMAs / commits of a slice (no per-instruction election loops in the SASS).
+    {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(&w_bar, 0);
       mbar_wait(&tzero_bar, 0);                     // accumulator strip has been zeroed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t wbase = smem_u32(wsm);
       const uint32_t rbase = smem_u32(ring);
+      // descriptor words: only the start-address field (low 14 bits of the low word, 16 B units) changes per MMA
+      const uint32_t a_hi = ((uint32_t)(HX * 16) >> 4) | (1u << 14);          // SBO = one halo row, version 1
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B between n-groups
+      const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;                // LBO = NP*16 B between the K halves
+      const uint32_t a_lbo_planes = ((uint32_t)PLANE_STRIDE >> 4) << 16;      // Cin >= 16: K halves are two planes
+      const uint32_t wb16 = wbase >> 4;
+      const int kcs = planes >> 1;
       int slot = 0; uint32_t ph = 0;
       for (int s = 0; s < nslices; ++s) {
         mbar_wait(&full_bar[slot], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // columns of output slices s (kz=0), s-1 (kz=1), s-2 (kz=2) are adjacent
         const uint32_t d_tmem = tmem_base + (uint32_t)((a.zcap + 1 - s) * CP);
-        const uint32_t sbase = rbase + (uint32_t)slot * slot_bytes;
-        int step = 0;
-        if (a.cin8) {
+        const uint32_t sb16 = (rbase + (uint32_t)slot * slot_bytes) >> 4;
+        if (elect_one()) {
+          uint32_t blo = wb16 | b_lbo;
+          if (a.cin8) {
 #pragma unroll
-          for (int p = 0; p < 5; ++p) {
-            const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
-            const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3)) * 16u;
-            const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3)) * 16u;
-            const uint32_t lbo = (t1 == t0) ? 0u : (o1 - o0);
-            umma_bf16(d_tmem, umma_desc(sbase + o0, lbo, HX * 16), umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, 1u);
-            ++step;
-          }
-        } else {
-          const int kcs = planes >> 1;
-          for (int t = 0; t < 9; ++t) {
-            const uint32_t o = (uint32_t)((t / 3) * HX + (t % 3)) * 16u;
-            for (int kc = 0; kc < kcs; ++kc) {
-              umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(2 * kc) * PLANE_STRIDE + o, PLANE_STRIDE, HX * 16),
-                        umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, 1u);
-              ++step;
+            for (int p = 0; p < 5; ++p) {
+              const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
+              const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3));
+              const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3));
+              const uint32_t alo = (sb16 + o0) | ((o1 - o0) << 16);       // LBO = distance between the two taps (0: dummy half)
+              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
+              blo += (uint32_t)(NP * 32) >> 4;
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              uint32_t alo = (sb16 + (uint32_t)((t / 3) * HX + (t % 3))) | a_lbo_planes;
+              for (int kc = 0; kc < kcs; ++kc) {
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
+                alo += (uint32_t)(2 * PLANE_STRIDE) >> 4;
+                blo += (uint32_t)(NP * 32) >> 4;
+              }
             }
           }
+          umma_commit(&empty_bar[slot]);                       // the input slice is consumed by this batch only
+          if (s >= 2) umma_commit(&tfull_bar[s - 2]);          // output slice s-2 has received its three kz parts
         }
-        umma_commit(&empty_bar[slot]);                       // the input slice is consumed by this batch only
-        if (s >= 2) umma_commit(&tfull_bar[s - 2]);          // output slice s-2 has received its three kz parts
+        __syncwarp();
         if (++slot == RING3) { slot = 0; ph ^= 1u; }
       }
     }
@@ -304,10 +318,16 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   CUtensorMap m0, m1;
-  if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
-  if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
-  else m1 = m0;
-  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)RING3 * (cin / 8) * PLANE_STRIDE + 1024;
+  if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
+  if (a.C1) { if (!tem_make_map_plane(&m1, &t.merged1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
+  else { m1 = m0; t.merged1 = t.merged0; }
+  // bytes in flight hide the ~2 us TMA round trip (Little's law): ring as deep as ~48 KB per CTA allow
+  static const char* ring_s = getenv("TEM_TC3_RING");
+  int ring = ring_s ? atoi(ring_s) : (int)((48 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));
+  if (ring > RING3_MAX) ring = RING3_MAX;
+  if (ring < 4) ring = 4;
+  t.ring = ring;
+  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)ring * (cin / 8) * PLANE_STRIDE + 1024;
   const unsigned grid = (unsigned)(cols * t.nzc);
   static bool attr[3] = {false, false, false};
 #define LAUNCH_TC3(CPV, IDX)                                                                                            \

@@ -41,6 +41,7 @@ struct S2Args {
   int Q[3];                    // UP: q extents; DOWN: = L
   int pad;                     // 0 or 1 (all axes)
   int planes;                  // Cin / 8
+  int merged;                  // UP: map folds (channel, x) when Cin == 8
   int shift[3];                // tensor coordinate = conv-input coordinate + shift
   int cin8;
   const bf16* wpacked; int wbytes;
@@ -146,7 +147,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * SUB_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         for (int p = 0; p < planes; ++p)
-          tma_load_5d(dst + p * SUB_STRIDE, &map0, &full_bar[slot], p * 8, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 - 1 + s + a.shift[0], b);
+          tma_load_plane(dst + p * SUB_STRIDE, &map0, &full_bar[slot], a.merged, p, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 - 1 + s + a.shift[0], b);
         if (++slot == RING) { slot = 0; ph ^= 1u; }
       }
     }
@@ -544,7 +545,8 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   CUtensorMap m0;
-  if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, up ? 1 : 2)) return cudaErrorInvalidValue;
+  if (up) { if (!tem_make_map_plane(&m0, &t.merged, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue; }
+  else if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)(cols * t.nzc);
   static bool attr[5] = {false, false, false, false, false};
 #define LAUNCH_S2(KERNEL, IDX)                                                                                          \

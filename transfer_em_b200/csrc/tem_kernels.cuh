@@ -130,6 +130,10 @@ cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st);
 bool wgrad_mma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);
 
+// wgrad_tc.cu: tcgen05 weight gradient of the 3x3x3 stride-1 convolutions (MN-major operands, rows of the tile as dy taps)
+bool wgrad_tc_supported(const WgradArgs& a);
+cudaError_t launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);
+
 // wgrad_tma.cu: TMA-staged, z-marching version of the tensor-core weight gradient
 bool wgrad_tma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tma(const WgradArgs& a, cudaStream_t st);

@@ -336,7 +336,9 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     static const bool no_mma = getenv("TEM_NO_WGRAD_MMA") != nullptr, no_c1 = getenv("TEM_NO_WGRAD_C1") != nullptr;   // debug knobs
     // TMA-ring variant (wgrad_tma.cu): measured slower than the cp.async tiles at wf=8 (profiles/README.md), opt-in
     static const bool use_tma = getenv("TEM_WGRAD_TMA") != nullptr;
-    if (h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) TEM_CUDA(launch_wgrad_tma(a, st));
+    static const bool no_wtc = getenv("TEM_NO_WGRAD_TC") != nullptr;   // debug knob: 3x3x3 weight gradients on the mma.sync kernel
+    if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) TEM_CUDA(launch_wgrad_tc(a, st));
+    else if (h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) TEM_CUDA(launch_wgrad_tma(a, st));
     else if (h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
     else if (h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) TEM_CUDA(launch_wgrad_c1(a, st));
     else TEM_CUDA(launch_wgrad_direct(a, st));

@@ -1,0 +1,296 @@
+// tcgen05 weight gradient of the 3x3x3 stride-1 VALID convolutions (models/utils.py:73,122; generator.py:54-110):
+//   dw[(dz,dy,dx)][ca][cb] = sum_{b,v} x[b, v + (dz,dy,dx)][ca] * g[b, v][cb]            
+//
+// GEMM view: D[M][N] += A[M][K] * B[N][K]^T with K = 16 consecutive x-voxels of one (z, y) row.  Both operands are
+// read in their natural channels-last layout as MN-MAJOR UMMA operands: a core matrix is 8 voxels (K) x 8 channels
+// (16 B, MN), i.e. exactly the [voxel][8 channels] plane layout TMA writes.  The taps are carried by the 8-channel
+// GROUPS of the M and N dimensions, which only need ONE uniform stride each:
+//   * M groups = (channel plane, row) of the x tile: group stride = one row of the tile.  With R_A rows per plane the
+//     MMA sees x rows y0 .. y0+R_A-1 at once;
+//   * N groups = (channel plane, row) of the g tile: rows y0 .. y0+RB-1.
+//   Block (x row i, g row j) of D is the partial sum of tap dy = i - j over the voxels of g row j: the three
+//   diagonals dy = 0, 1, 2 are useful, everything else is discarded.  Different j are different voxels, so nothing is
+//   computed twice; the diagonal blocks are added up in the epilogue.
+//   * dx is a shifted start address of the g operand (16 B per voxel), dz a different g slice: 9 (dz,dx) accumulators
+//     of N columns each stay resident in TMEM for the whole CTA.
+// One CTA owns (sample, RB g-rows, a chunk of x z-slices, the full x extent); per x z-slice the x tile and the newest
+// g slice arrive through TMA rings (OOB zero fill gives the virtual zero padding of g), one thread issues
+// (runs x 9) M64/128 x N x K16 MMAs, and after the last slice four warps fold the diagonals of the 9 accumulators
+// into a shared-memory dw image that leaves with one atomicAdd per weight and CTA.
+// wgrad_mma.cu explains why taps cannot be the M dimension directly; this kernel side-steps that by letting rows of
+// the tile (uniformly strided) play the role of the dy taps.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "tem_kernels.cuh"
+#include "ptx_sm100.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int XR_MAX = 8, DR_MAX = 10;       // ring depths (x slices, g slices) are chosen per launch
+constexpr int kThreads = 192;
+
+struct WtArgs {
+  int B, L[3];                 // extent of g (z,y,x)
+  int pa, pb;                  // 8-channel planes of x / g
+  int RA, RB;                  // rows per plane in the x tile / in the g tile (RB = useful g rows per CTA)
+  int M, N;                    // MMA shape: M = 8*pa*RA (64 or 128), N = 8*pb*RB
+  int NR;                      // 16-voxel runs along x
+  int WA, WB;                  // tile widths in voxels: WA = 16*NR, WB = 16*NR + 8 (g tile starts at x = -2)
+  int shift[3];                // x tensor coordinate = x-window coordinate + shift
+  int nrg, nzc, zc;            // row groups, z chunks, x slices per chunk
+  int units;                   // work units (sample, row group, z chunk); CTAs are persistent over them
+  int XR, DR;                  // ring depths
+  int tmem_cols;
+  int xa_bytes, gb_bytes;      // bytes of one ring slot
+  float* dw; long long ws_tap, ws_a, ws_b;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SWIZZLE_NONE MN-major: ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16 B units - SBO between 8-channel groups, LBO between 8-voxel K groups
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const WtArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t xfull[XR_MAX], xempty[XR_MAX], gfull[DR_MAX], gempty[DR_MAX], done_bar;
+  const int XR = a.XR, DR = a.DR;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* xring = smem;
+  uint8_t* gring = smem + (size_t)a.XR * a.xa_bytes;
+
+  // work unit u -> (sample b, first g row y0, first x slice zx0, slices nzx)
+  auto decode = [&](int u, int& b, int& y0, int& zx0, int& nzx) {
+    const int zc_i = u % a.nzc; u /= a.nzc;
+    const int rg = u % a.nrg; u /= a.nrg;
+    b = u; y0 = rg * a.RB; zx0 = zc_i * a.zc;
+    nzx = min(a.zc, a.L[0] + 2 - zx0);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XR; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < DR; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gslot = 0; uint32_t gph = 0; int xslot = 0; uint32_t xph = 0;
+      for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        int b, y0, zx0, nzx; decode(u, b, y0, zx0, nzx);
+        // g slices zx0-2 .. zx0+nzx-1 (index i = zd - (zx0-2)); x slices zx0 .. zx0+nzx-1 (step s)
+        auto load_g = [&](int i) {
+          mbar_wait(&gempty[gslot], gph ^ 1u);
+          mbar_arrive_expect_tx(&gfull[gslot], (uint32_t)a.gb_bytes);
+          uint8_t* dst = gring + (size_t)gslot * a.gb_bytes;
+          const int plane_bytes = a.RB * a.WB * 16;
+          for (int p = 0; p < a.pb; ++p)
+            tma_load_5d(dst + p * plane_bytes, &mapg, &gfull[gslot], p * 8, -2, y0, zx0 - 2 + i, b);
+          if (++gslot == DR) { gslot = 0; gph ^= 1u; }
+        };
+        load_g(0); load_g(1);
+        for (int s = 0; s < nzx; ++s) {
+          load_g(s + 2);
+          mbar_wait(&xempty[xslot], xph ^ 1u);
+          mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
+          uint8_t* dst = xring + (size_t)xslot * a.xa_bytes;
+          const int plane_bytes = a.RA * a.WA * 16;
+          for (int p = 0; p < a.pa; ++p)
+            tma_load_5d(dst + p * plane_bytes, &mapx, &xfull[xslot], p * 8, a.shift[2], y0 + a.shift[1], zx0 + s + a.shift[0], b);
+          if (++xslot == XR) { xslot = 0; xph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // the whole warp runs the issue loop convergently (uniform values stay in uniform registers); one elected lane
+    // executes the MMAs / commits
+    {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+      // descriptors are affine in the start address: only the low word (start >> 4, LBO) changes inside the loops, so
+      // the single issuing thread spends a couple of integer adds per MMA instead of rebuilding 64-bit descriptors
+      const uint32_t lo_fixed = (128u >> 4) << 16;                                   // LBO = 128 B (next 8 voxels)
+      const uint32_t a_hi = (((uint32_t)a.WA * 16u) >> 4) | (1u << 14), b_hi = (((uint32_t)a.WB * 16u) >> 4) | (1u << 14);   // SBO, version
+      const uint32_t xbase16 = smem_u32(xring) >> 4, gbase16 = smem_u32(gring) >> 4;
+      const uint32_t xa16 = (uint32_t)a.xa_bytes >> 4, gb16 = (uint32_t)a.gb_bytes >> 4;
+      const uint32_t N = (uint32_t)a.N;
+      int gwslot = 0; uint32_t gwph = 0;                    // next g slot to wait for
+      int xslot = 0; uint32_t xph = 0;
+      int gold = 0;                                         // ring slot of the oldest live g slice
+      uint32_t acc = 0u;
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t accf) {
+        if (!elect_one()) return;
+        uint64_t ad, bd;
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(ad) : "r"(alo), "r"(a_hi));
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(bd) : "r"(blo), "r"(b_hi));
+        umma_bf16(d, ad, bd, idesc, accf);
+      };
+      for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+        int b, y0, zx0, nzx; decode(u, b, y0, zx0, nzx);
+        // the first two g slices of the unit
+        for (int i = 0; i < 2; ++i) { mbar_wait(&gfull[gwslot], gwph); if (++gwslot == DR) { gwslot = 0; gwph ^= 1u; } }
+        for (int s = 0; s < nzx; ++s) {
+          mbar_wait(&gfull[gwslot], gwph); if (++gwslot == DR) { gwslot = 0; gwph ^= 1u; }
+          mbar_wait(&xfull[xslot], xph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          int g1s = gold + 1; if (g1s >= DR) g1s -= DR;
+          int g2s = gold + 2; if (g2s >= DR) g2s -= DR;
+          // dz = 0, 1, 2 read g index s+2, s+1, s  (zd = zx - dz); +2 voxels: the g tile starts at x = -2
+          const uint32_t b0 = (gbase16 + (uint32_t)g2s * gb16 + 2u) | lo_fixed;
+          const uint32_t b1 = (gbase16 + (uint32_t)g1s * gb16 + 2u) | lo_fixed;
+          const uint32_t b2 = (gbase16 + (uint32_t)gold * gb16 + 2u) | lo_fixed;
+          uint32_t alo = (xbase16 + (uint32_t)xslot * xa16) | lo_fixed;
+          for (int r = 0; r < a.NR; ++r) {
+            const uint32_t ro = (uint32_t)r * 16u;           // 16 voxels = 256 B = 16 descriptor units
+            mma(tmem_base + 0 * N, alo, b0 + ro, acc);      mma(tmem_base + 1 * N, alo, b0 + ro - 1u, acc); mma(tmem_base + 2 * N, alo, b0 + ro - 2u, acc);
+            mma(tmem_base + 3 * N, alo, b1 + ro, acc);      mma(tmem_base + 4 * N, alo, b1 + ro - 1u, acc); mma(tmem_base + 5 * N, alo, b1 + ro - 2u, acc);
+            mma(tmem_base + 6 * N, alo, b2 + ro, acc);      mma(tmem_base + 7 * N, alo, b2 + ro - 1u, acc); mma(tmem_base + 8 * N, alo, b2 + ro - 2u, acc);
+            alo += 16u; acc = 1u;
+          }
+          if (elect_one()) {
+            umma_commit(&xempty[xslot]);
+            umma_commit(&gempty[gold]);                      // g index s (zd = zx - 2) is not needed by later x slices
+            if (s == nzx - 1) { umma_commit(&gempty[g1s]); umma_commit(&gempty[g2s]); }   // end of the unit: the last two g slices too
+          }
+          __syncwarp();
+          if (++xslot == XR) { xslot = 0; xph ^= 1u; }
+          if (++gold == DR) gold = 0;
+        }
+        gold += 2; if (gold >= DR) gold -= DR;               // the next unit starts with fresh g slices
+      }
+      if (elect_one()) umma_commit(&done_bar);
+      __syncwarp();
+    }
+  }
+  // ---- epilogue: fold the useful diagonals of the 9 accumulators into a shared dw image, then one atomic per weight
+  float* red = reinterpret_cast<float*>(smem);
+  const int Ca = a.pa * 8, Cb = a.pb * 8;
+  const int nred = 27 * Ca * Cb;
+  if (warp >= 2) {
+    mbar_wait(&done_bar, 0);                                 // all MMAs retired: rings are free, accumulators final
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int i = threadIdx.x - 64; i < nred; i += 128) red[i] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int q = warp & 3;
+    // M = 128: TMEM lane = row.  M = 64: rows 16q .. 16q+15 live in lanes 0..15 of subpartition q.
+    const int m = (a.M == 128) ? q * 32 + lane : q * 16 + (lane & 15);
+    const bool rowok = (a.M == 128) || lane < 16;
+    const int gm = m >> 3, pA = gm / a.RA, gi = gm % a.RA, ca = pA * 8 + (m & 7);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ngn = a.N >> 3;
+    for (int acc = 0; acc < 9; ++acc) {
+      const int dz = acc / 3, dx = acc % 3;
+      for (int gn = 0; gn < ngn; ++gn) {
+        uint32_t r[8];
+        tmem_ld8(lane_base + (uint32_t)(acc * a.N + gn * 8), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int pB = gn / a.RB, j = gn % a.RB;
+        const int ty = gi - j;
+        if (rowok && ty >= 0 && ty < 3) {
+          float* dst = red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * Cb + pB * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) atomicAdd(dst + u, __uint_as_float(r[u]));
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = threadIdx.x - 64; i < nred; i += 128) {
+      const float v = red[i];
+      if (v != 0.f) {
+        const int cb = i % Cb, t = i / Cb, cA = t % Ca, tap = t / Ca;
+        atomicAdd(a.dw + (long long)tap * a.ws_tap + (long long)cA * a.ws_a + (long long)cb * a.ws_b, v);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+  }
+}
+
+bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
+  memset(&t, 0, sizeof(t));
+  t.B = w.B; for (int i = 0; i < 3; ++i) { t.L[i] = w.L[i]; t.shift[i] = w.S.shift[i]; }
+  t.pa = w.Ca / 8; t.pb = w.Cb / 8;
+  t.M = (t.pa == 4) ? 128 : 64;
+  t.RA = (t.M / 8) / t.pa;
+  int rb = t.RA - 2;
+  while (rb > 1 && rb * w.Cb > 56) --rb;
+  if (t.M == 128) while (rb > 1 && (rb * w.Cb) % 16) --rb;
+  t.RB = rb; t.N = rb * w.Cb;
+  if (t.N > 56 || (t.M == 128 && t.N % 16)) return false;
+  t.NR = (w.L[2] + 2 + 15) / 16;
+  t.WA = 16 * t.NR; t.WB = 16 * t.NR + 8;
+  if (t.WB > 256) return false;
+  t.xa_bytes = t.pa * t.RA * t.WA * 16; t.gb_bytes = t.pb * t.RB * t.WB * 16;
+  int cols = 32; while (cols < 9 * t.N) cols <<= 1;
+  t.tmem_cols = cols;
+  // rings as deep as ~150 KB allow (one CTA per SM anyway: the accumulators take most of TMEM)
+  t.XR = 3; t.DR = 5;
+  while (t.XR < XR_MAX && (size_t)(t.XR + 1) * t.xa_bytes + (size_t)(t.DR + 1) * t.gb_bytes <= 150 * 1024) { ++t.XR; ++t.DR; }
+  smem = (size_t)t.XR * t.xa_bytes + (size_t)t.DR * t.gb_bytes + 1024;
+  const size_t red = (size_t)27 * w.Ca * w.Cb * 4;
+  if (red + 1024 > smem) smem = red + 1024;
+  return smem <= 200 * 1024;
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const WgradArgs& w) {
+  if (w.S.dtype != DT_BF16 || w.p_dtype != DT_BF16 || w.S.origins || w.use_lut) return false;
+  for (int i = 0; i < 3; ++i) if (w.k[i] != 3 || w.stride[i] != 1 || w.pad[i] != 0 || w.p_off[i] != 0) return false;
+  if (!(w.Ca == 8 || w.Ca == 16 || w.Ca == 32) || !(w.Cb == 8 || w.Cb == 16 || w.Cb == 32)) return false;
+  if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
+  if (w.PZ != w.L[0] || w.PY != w.L[1] || w.PX != w.L[2]) return false;      // OOB zero fill is the padding of g
+  if (w.p_bstride != (long long)w.L[0] * w.L[1] * w.L[2] * w.Cb) return false;
+  if (w.S.bstride != (long long)w.S.Z * w.S.Y * w.S.X * w.S.C) return false;
+  WtArgs t; size_t smem;
+  if (!plan(w, t, smem)) return false;
+  return tem_get_encode() != nullptr;
+}
+
+cudaError_t launch_wgrad_tc(const WgradArgs& w, cudaStream_t st) {
+  WtArgs t; size_t smem;
+  if (!plan(w, t, smem)) return cudaErrorInvalidConfiguration;
+  if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
+  t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
+  t.nrg = (w.L[1] + t.RB - 1) / t.RB;
+  // z chunks: one CTA per SM (the accumulators take most of TMEM); pick the chunk count with the best wave efficiency
+  const long long cols = (long long)w.B * t.nrg;
+  const int nslices = w.L[0] + 2;
+  int best = 1; double best_eff = -1.0;
+  for (int nzc = 1; nzc <= nslices && nzc <= 64; ++nzc) {
+    const int zc = (nslices + nzc - 1) / nzc;
+    if (zc < 3 && nzc > 1) break;
+    const int real = (nslices + zc - 1) / zc;
+    const long long units = cols * real;
+    const long long waves = (units + 147) / 148;
+    const double eff = (double)units / (double)(waves * 148) * (double)zc / (double)(zc + 2);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = nzc; }
+  }
+  t.zc = (nslices + best - 1) / best; t.nzc = (nslices + t.zc - 1) / t.zc;
+  CUtensorMap mx, mg;
+  if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, t.WA, t.RA)) return cudaErrorInvalidValue;
+  if (!tem_make_map_5d(&mg, w.P, w.B, w.PZ, w.PY, w.PX, w.p_C, t.WB, t.RB)) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) { cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr = true; }
+  t.units = (int)(cols * t.nzc);
+  const unsigned grid = (unsigned)(t.units < 148 ? t.units : 148);
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mx, mg, t); ++g_tem_launches;
+  return cudaGetLastError();
+}
