@@ -173,15 +173,27 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     mbar_arrive(&tzero_bar);
     const bool has_c8[4] = {0 < a.Cout, 8 < a.Cout, 16 < a.Cout, 24 < a.Cout};
-    for (int zo = 0; zo < nz; ++zo) {
-      const int oz = z0 + zo;
-      // operands of the fused epilogue are fetched BEFORE waiting for the accumulator (hides the global-load latency)
-      uint4 refq[CP / 8];
-      if (a.ref && inside) {
-        const long long ro = ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+    // Operands of the fused epilogue (stored activation of the LeakyReLU' factor) are fetched PF output slices ahead of
+    // their use: with one 16 B load per thread and slice in flight an SM keeps only ~4 KB of this stream outstanding,
+    // far below what the ~2 us round trip needs (Little's law); PF slices ahead restore the bandwidth.
+    constexpr int PF = 32 / CP >= 2 ? 32 / CP * 2 : 2;      // CP = 8: 8 slices, 16: 4, 32: 2  (32 registers)
+    uint4 refq[PF][CP / 8];
+    const long long ref_zstride = (long long)a.RY * a.RX * a.ref_C;
+    const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+    auto fetch_ref = [&](int zo, uint4* q) {
+      if (a.ref && inside && zo < nz) {
 #pragma unroll
-        for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ro + c * 8));
+        for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) q[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ref_base + (long long)zo * ref_zstride + c * 8));
       }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) fetch_ref(u, refq[u]);
+    for (int zb = 0; zb < nz; zb += PF) {
+#pragma unroll
+    for (int pu = 0; pu < PF; ++pu) {
+      const int zo = zb + pu;
+      if (zo >= nz) break;
+      const int oz = z0 + zo;
       mbar_wait(&tfull_bar[zo], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[CP];
@@ -198,12 +210,13 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         for (int c = 0; c < CP; c += 8) {
           if (c < a.Cout) {
             float f[8];
-            unpack8(refq[c / 8], f);
+            unpack8(refq[pu][c / 8], f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
           }
         }
       }
+      fetch_ref(zo + PF, refq[pu]);
       if (a.drop_key) {
         const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
 #pragma unroll
@@ -229,6 +242,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           *reinterpret_cast<uint4*>(op + c) = pk;
         }
       }
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -305,7 +319,8 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   // accumulator strip: (zcap + 5) column groups of CP columns; 256 columns keep two CTAs per SM when that leaves a
   // useful chunk, otherwise the whole TMEM (one CTA per SM)
   static const char* c16 = getenv("TEM_TC3_COLS16");
-  t.tmem_cols = (cp == 8) ? 256 : (cp == 16 ? (c16 ? atoi(c16) : 256) : 512);   // measured: 2 CTAs/SM beat a longer z-chunk at CP = 16
+  static const char* c8 = getenv("TEM_TC3_COLS8");
+  t.tmem_cols = (cp == 8) ? (c8 ? atoi(c8) : 256) : (cp == 16 ? (c16 ? atoi(c16) : 256) : 512);   // measured: 2 CTAs/SM beat a longer z-chunk at CP = 16
   t.zcap = t.tmem_cols / cp - 5;
   if (t.zcap > kMaxChunk) t.zcap = kMaxChunk;
   const long long cols = (long long)a.B * t.ntx * t.nty;

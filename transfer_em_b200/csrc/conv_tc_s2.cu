@@ -152,11 +152,14 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // convergent issue loop: the whole warp waits, one elected lane issues the MMAs / commits of a q-slice
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(&w_bar, 0);
-      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t wb16 = smem_u32(wsm) >> 4;
       const uint32_t rbase = smem_u32(ring);
+      const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;
+      const uint32_t a_lbo = a.cin8 ? (1u << 16) : (((uint32_t)SUB_STRIDE >> 4) << 16);   // K halves: next voxel / next plane
       int waited = 0, wslot = 0, zslot = 0; uint32_t wph = 0;
       const int kcs = planes >> 1;
       for (int zo = 0; zo < nz; ++zo) {
@@ -164,27 +167,34 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NP;
-        uint32_t acc = 0;
-        int step = 0;
-        for (int mz = 0; mz < 2; ++mz) {
-          int sl = zslot + mz; if (sl >= RING) sl -= RING;
-          const uint32_t sbase = rbase + (uint32_t)sl * slot_bytes;
-          for (int my = 0; my < 2; ++my) {
-            if (a.cin8) {          // one plane: the K=16 step covers the taps mx = 0, 1 (adjacent voxels)
-              umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(my * SXV) * 16u, 16u, ROW_B), umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, acc);
-              acc = 1; ++step;
-            } else {
-              for (int mx = 0; mx < 2; ++mx)
-                for (int kc = 0; kc < kcs; ++kc) {
-                  umma_bf16(d_tmem, umma_desc(sbase + (uint32_t)(2 * kc) * SUB_STRIDE + (uint32_t)(my * SXV + mx) * 16u, SUB_STRIDE, ROW_B),
-                            umma_desc(wbase + (uint32_t)step * (NP * 32), NP * 16, 128), idesc, acc);
-                  acc = 1; ++step;
+        int sl1 = zslot + 1; if (sl1 >= RING) sl1 -= RING;
+        if (elect_one()) {
+          uint32_t acc = 0;
+          uint32_t blo = wb16 | b_lbo;
+#pragma unroll
+          for (int mz = 0; mz < 2; ++mz) {
+            const uint32_t sb16 = (rbase + (uint32_t)(mz ? sl1 : zslot) * slot_bytes) >> 4;
+#pragma unroll
+            for (int my = 0; my < 2; ++my) {
+              if (a.cin8) {          // one plane: the K=16 step covers the taps mx = 0, 1 (adjacent voxels)
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | ((sb16 + (uint32_t)(my * SXV)) | a_lbo), ((uint64_t)b_hi << 32) | blo, idesc, acc);
+                acc = 1; blo += (uint32_t)(NP * 32) >> 4;
+              } else {
+#pragma unroll
+                for (int mx = 0; mx < 2; ++mx) {
+                  uint32_t alo = (sb16 + (uint32_t)(my * SXV + mx)) | a_lbo;
+                  for (int kc = 0; kc < kcs; ++kc) {
+                    umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+                    acc = 1; alo += (uint32_t)(2 * SUB_STRIDE) >> 4; blo += (uint32_t)(NP * 32) >> 4;
+                  }
                 }
+              }
             }
           }
+          umma_commit(&tfull_bar[zo & 1]);
+          umma_commit(&empty_bar[zslot]);      // input slice zo-1 is not used by later outputs
         }
-        umma_commit(&tfull_bar[zo & 1]);
-        umma_commit(&empty_bar[zslot]);      // input slice zo-1 is not used by later outputs
+        __syncwarp();
         if (++zslot == RING) zslot = 0;
       }
     }
@@ -319,11 +329,14 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // convergent issue loop (see the UP kernel)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(&w_bar, 0);
-      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t wb16 = smem_u32(wsm) >> 4;
       const uint32_t rbase = smem_u32(ring);
+      const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_lbo = ((uint32_t)(NPAD * 16) >> 4) << 16;
+      const uint32_t a_lbo = a.cin8 ? (1u << 16) : (((uint32_t)SUB_STRIDE >> 4) << 16);
       int waited = 0, wslot = 0, zslot = 0; uint32_t wph = 0;
       const int kcs = planes >> 1;
       for (int zo = 0; zo < nz; ++zo) {
@@ -331,32 +344,40 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NPAD;
-        uint32_t acc = 0;
-        int step = 0;
-        for (int kz = 0; kz < 4; ++kz) {
-          int sl = zslot + kz; if (sl >= RING) sl -= RING;
-          const uint32_t sbase = rbase + (uint32_t)sl * slot_bytes;
-          for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t tbase = sbase + (uint32_t)(rr * planes) * SUB_STRIDE;
-            for (int my = 0; my < 2; ++my) {
-              if (a.cin8) {
-                umma_bf16(d_tmem, umma_desc(tbase + (uint32_t)(my * SXV) * 16u, 16u, ROW_B), umma_desc(wbase + (uint32_t)step * (NPAD * 32), NPAD * 16, 128), idesc, acc);
-                acc = 1; ++step;
-              } else {
-                for (int mx = 0; mx < 2; ++mx)
-                  for (int kc = 0; kc < kcs; ++kc) {
-                    umma_bf16(d_tmem, umma_desc(tbase + (uint32_t)(2 * kc) * SUB_STRIDE + (uint32_t)(my * SXV + mx) * 16u, SUB_STRIDE, ROW_B),
-                              umma_desc(wbase + (uint32_t)step * (NPAD * 32), NPAD * 16, 128), idesc, acc);
-                    acc = 1; ++step;
+        int s1 = zslot + 1; if (s1 >= RING) s1 -= RING;
+        if (elect_one()) {
+          uint32_t acc = 0;
+          uint32_t blo = wb16 | b_lbo;
+#pragma unroll
+          for (int kz = 0; kz < 4; ++kz) {
+            int sl = zslot + kz; if (sl >= RING) sl -= RING;
+            const uint32_t sb16 = (rbase + (uint32_t)sl * slot_bytes) >> 4;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const uint32_t tb16 = sb16 + (((uint32_t)(rr * planes) * SUB_STRIDE) >> 4);
+#pragma unroll
+              for (int my = 0; my < 2; ++my) {
+                if (a.cin8) {
+                  umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | ((tb16 + (uint32_t)(my * SXV)) | a_lbo), ((uint64_t)b_hi << 32) | blo, idesc, acc);
+                  acc = 1; blo += (uint32_t)(NPAD * 32) >> 4;
+                } else {
+#pragma unroll
+                  for (int mx = 0; mx < 2; ++mx) {
+                    uint32_t alo = (tb16 + (uint32_t)(my * SXV + mx)) | a_lbo;
+                    for (int kc = 0; kc < kcs; ++kc) {
+                      umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+                      acc = 1; alo += (uint32_t)(2 * SUB_STRIDE) >> 4; blo += (uint32_t)(NPAD * 32) >> 4;
+                    }
                   }
+                }
               }
             }
           }
+          umma_commit(&tfull_bar[zo & 1]);
+          umma_commit(&empty_bar[zslot]);                          // input slices 2zo and 2zo+1 are done
+          umma_commit(&empty_bar[s1]);
         }
-        umma_commit(&tfull_bar[zo & 1]);
-        umma_commit(&empty_bar[zslot]);                          // input slices 2zo and 2zo+1 are done
-        int s1 = zslot + 1; if (s1 >= RING) s1 -= RING;
-        umma_commit(&empty_bar[s1]);
+        __syncwarp();
         zslot += 2; if (zslot >= RING) zslot -= RING;
       }
     }

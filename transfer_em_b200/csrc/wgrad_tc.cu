@@ -191,23 +191,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
     const int gm = m >> 3, pA = gm / a.RA, gi = gm % a.RA, ca = pA * 8 + (m & 7);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ngn = a.N >> 3;
-    for (int acc = 0; acc < 9; ++acc) {
-      const int dz = acc / 3, dx = acc % 3;
-      for (int gn = 0; gn < ngn; ++gn) {
-        uint32_t r[8];
-        tmem_ld8(lane_base + (uint32_t)(acc * a.N + gn * 8), r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int pB = gn / a.RB, j = gn % a.RB;
-        const int ty = gi - j;
-        if (rowok && ty >= 0 && ty < 3) {
-          float* dst = red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * Cb + pB * 8;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) atomicAdd(dst + u, __uint_as_float(r[u]));
+    // Round j folds the column groups of g row j: in one round an address (tap, ca, cb) is touched by exactly one
+    // thread (x row i <-> dy = i - j), so plain read-modify-writes suffice; rounds are separated by a named barrier.
+    for (int j = 0; j < a.RB; ++j) {
+      const int ty = gi - j;
+      const bool use = rowok && ty >= 0 && ty < 3;
+      for (int acc = 0; acc < 9; ++acc) {
+        const int dz = acc / 3, dx = acc % 3;
+        for (int pB = 0; pB < a.pb; ++pB) {
+          uint32_t r[8];
+          tmem_ld8(lane_base + (uint32_t)(acc * a.N + (pB * a.RB + j) * 8), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (use) {
+            float4* dst = reinterpret_cast<float4*>(red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * Cb + pB * 8);
+            float4 v0 = dst[0], v1 = dst[1];
+            v0.x += __uint_as_float(r[0]); v0.y += __uint_as_float(r[1]); v0.z += __uint_as_float(r[2]); v0.w += __uint_as_float(r[3]);
+            v1.x += __uint_as_float(r[4]); v1.y += __uint_as_float(r[5]); v1.z += __uint_as_float(r[6]); v1.w += __uint_as_float(r[7]);
+            dst[0] = v0; dst[1] = v1;
+          }
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int i = threadIdx.x - 64; i < nred; i += 128) {
+    // every CTA starts its pass over the dw image at a different offset: fewer same-address collisions in L2
+    const int rot = (int)(((long long)blockIdx.x * nred / gridDim.x) & ~127LL);
+    for (int i0 = threadIdx.x - 64; i0 < nred; i0 += 128) {
+      int i = i0 + rot; if (i >= nred) i -= nred;
       const float v = red[i];
       if (v != 0.f) {
         const int cb = i % Cb, t = i / Cb, cA = t % Ca, tap = t / Ca;
@@ -290,7 +299,12 @@ cudaError_t launch_wgrad_tc(const WgradArgs& w, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr = true; }
   t.units = (int)(cols * t.nzc);
-  const unsigned grid = (unsigned)(t.units < 148 ? t.units : 148);
+  // every CTA ends with a pass of 27*Ca*Cb atomics: small layers get fewer, longer-lived CTAs (>= ~512 MMAs each)
+  static const char* mpc_s = getenv("TEM_WGRAD_TC_MPC");
+  const long long mmas = (long long)t.units * t.zc * t.NR * 9;
+  long long want = mmas / (mpc_s ? atoi(mpc_s) : 96);
+  if (want < 1) want = 1; if (want > 148) want = 148; if (want > t.units) want = t.units;
+  const unsigned grid = (unsigned)want;
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mx, mg, t); ++g_tem_launches;
   return cudaGetLastError();
 }
