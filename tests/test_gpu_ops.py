@@ -192,6 +192,11 @@ TC_CASES = [
     (8, 16, (12, 9, 10)),
     (32, 16, (5, 35, 27)),      # several y / x tiles with ragged edges
     (16, 32, (23, 10, 10)),     # z chunks
+    # wide layers (conv_tcw.cu): 32-channel output groups, Cin swept in 32-channel passes, several z chunks
+    (64, 64, (15, 19, 11)),
+    (128, 32, (6, 9, 10)),
+    (64, 96, (5, 18, 9)),
+    (96, 40, (14, 8, 8)),
 ]
 
 

@@ -112,6 +112,12 @@ size_t tc3_packed_bytes(int cin, int cout);
 cudaError_t tc3_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 
+// conv_tcw.cu: tcgen05 kernel for wide 3x3x3 stride-1 layers (Cin >= 64, 32-channel output groups, Cin swept in 32-channel passes)
+bool tcw_conv_supported(const ConvArgs& a);
+size_t tcw_packed_bytes(int cin, int cout);
+cudaError_t tcw_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
+cudaError_t launch_conv_tcw(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
+
 // conv_tc_s2.cu: tcgen05 kernels for the 4x4x4 stride-2 layers (strided conv / transposed conv, forward and data gradient)
 bool tc_s2_supported(const ConvArgs& a);
 size_t tc_s2_packed_bytes(const ConvArgs& a);

@@ -179,9 +179,11 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
 }
 
 static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  if (kind == 3) return tcw_pack_weights(a, dst, st);
   return kind == 2 ? tc_s2_pack_weights(a, dst, st) : (kind == 1 ? tc_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st));
 }
 static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
+  if (kind == 3) return launch_conv_tcw(a, wp, st);
   return kind == 2 ? launch_conv_tc_s2(a, wp, st) : (kind == 1 ? launch_conv_tc(a, wp, st) : launch_conv_tc3(a, wp, st));
 }
 
@@ -194,9 +196,10 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   static const bool gen1 = getenv("TEM_CONV_TC_GEN1") != nullptr;   // debug knob: first-generation kernel (one MMA batch per output slice)
   int kind = -1;                                                    // packed-weight tcgen05 kernels
   if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) kind = gen1 ? 1 : 0;
+  else if (h->cfg.use_tensor_cores && !no_tc && tcw_conv_supported(a)) kind = 3;
   else if (h->cfg.use_tensor_cores && !no_tc && !no_s2 && tc_s2_supported(a)) kind = 2;
   if (kind >= 0) {
-    const size_t bytes = kind == 2 ? tc_s2_packed_bytes(a) : (kind == 1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout));
+    const size_t bytes = kind == 3 ? tcw_packed_bytes(a.C0 + a.C1, a.Cout) : kind == 2 ? tc_s2_packed_bytes(a) : (kind == 1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout));
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
       static bool pool_kept = false;       // keep freed blocks in the default pool across synchronisations
