@@ -166,7 +166,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--infer-size", type=int, default=288, help="edge of the tiled-inference request (multiple of 36)")
+    ap.add_argument("--wf", type=int, default=8, help="width divisor of the model (8 = BASELINE config 3; 1 = config 4, 64/128/256 channels)")
+    ap.add_argument("--dim", type=int, default=74, help="patch edge (n = 2 mod 4; config 4 uses 110)")
     args = ap.parse_args()
+    global DIM, WF
+    DIM, WF = args.dim, args.wf
     # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -320,7 +324,8 @@ def main():
         line = {"metric": "train_voxels_per_s", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": "BASELINE config 3: 3D CycleGAN full train step, EM2EM(74, is3d, wf=8), focal losses, dropout on",
+                "config": {"workload": ("BASELINE config 3" if (WF, DIM) == (8, 74) else "BASELINE config 4 (single-GPU share)" if WF == 1 else "width sweep") +
+                                       f": 3D CycleGAN full train step, EM2EM({DIM}, is3d, wf={WF}), focal losses, dropout on",
                            "dimsize": DIM, "wf": WF, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "input": "uint8 patches, standardise fused into the first-layer kernels",
                            "l2": "per-step working set ~1.5 GB of activations >> 126 MB L2; 4 distinct input batches cycled"},

@@ -233,7 +233,11 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   static const bool no_c1 = getenv("TEM_NO_CONV_C1") != nullptr;     // debug knob
   if (h->cfg.use_tensor_cores && !no_c1 && conv_c1_supported(a)) { TEM_CUDA(launch_conv_c1(a, st)); return TEM_OK; }
   static const bool no_mma = getenv("TEM_NO_CONV_MMA") != nullptr;   // debug knob
-  if (h->cfg.use_tensor_cores && !no_mma && conv_mma_supported(a)) { TEM_CUDA(launch_conv_mma(a, st)); return TEM_OK; }
+  if (h->cfg.use_tensor_cores && !no_mma && conv_mma_supported(a)) {
+    const cudaError_t e = launch_conv_mma(a, st);
+    if (e != cudaErrorInvalidConfiguration) { TEM_CUDA(e); return TEM_OK; }
+    (void)cudaGetLastError();                 // the shape does not tile into shared memory: direct kernel
+  }
   TEM_CUDA(launch_conv_direct(a, st));
   return TEM_OK;
 }
@@ -340,11 +344,14 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     // TMA-ring variant (wgrad_tma.cu): measured slower than the cp.async tiles at wf=8 (profiles/README.md), opt-in
     static const bool use_tma = getenv("TEM_WGRAD_TMA") != nullptr;
     static const bool no_wtc = getenv("TEM_NO_WGRAD_TC") != nullptr;   // debug knob: 3x3x3 weight gradients on the mma.sync kernel
-    if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) TEM_CUDA(launch_wgrad_tc(a, st));
-    else if (h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) TEM_CUDA(launch_wgrad_tma(a, st));
-    else if (h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) TEM_CUDA(launch_wgrad_mma(a, st));
-    else if (h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) TEM_CUDA(launch_wgrad_c1(a, st));
-    else TEM_CUDA(launch_wgrad_direct(a, st));
+    // a kernel that cannot tile the shape (shared memory) answers cudaErrorInvalidConfiguration: the next one is tried
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) e = launch_wgrad_tc(a, st);
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) e = launch_wgrad_tma(a, st);
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) e = launch_wgrad_mma(a, st);
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) e = launch_wgrad_c1(a, st);
+    if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_wgrad_direct(a, st); }
+    TEM_CUDA(e);
   }
   return TEM_OK;
 }
