@@ -5,9 +5,9 @@
 //   form 1:  out[j] = sum_{k: (j+pad-k)%s==0} in[(j+pad-k)/s] w[k]      (conv dgrad, convT fwd): one CTA per output
 //            parity class, so every class is a dense 2x2x2 (k=4,s=2) gather with warp-uniform taps.
 // A rows are output positions: each ldmatrix row is the 16 B (8-channel) chunk of one input voxel in a cp.async-staged
-// halo, so stride, taps and parity classes are only address arithmetic.  Why not tcgen05 here: a stride-2 gather needs a
-// row stride of 2 voxels inside the 8-row core matrix, which the UMMA canonical layouts cannot express without a
-// space-to-depth copy of the input; that variant (TMA element-strides) is the planned follow-up.
+// halo, so stride, taps and parity classes are only address arithmetic.  The 4x4x4 stride-2 layers whose weights fit
+// beside the TMA ring now run on the tcgen05 kernels of conv_tc_s2.cu (TMA element strides do the space-to-depth
+// split); this kernel keeps the 32 -> 32 stride-2 forward layers (d4, d6), the 1x1 layers and the 2-D shapes.
 #include <string.h>
 #include "tem_kernels.cuh"
 

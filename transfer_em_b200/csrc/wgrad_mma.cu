@@ -2,11 +2,13 @@
 //   dw[tap][ca][cb] += sum_{b,p} S[b, s*p + tap - pad][ca] * P[b,p][cb]          
 // (conv: S = layer input, P = dy; transposed conv: S = dy, P = layer input - models/utils.py:73,80,129-130).
 //
-// Why warp-level mma.sync (m16n8k16, bf16 -> fp32) and not tcgen05 here: the GEMM is M = (tap, ca) x N = cb x
+// Used for the stride-2 / transposed / 1x1 layers and as the fall-back of wgrad_tc.cu (the tcgen05 kernel of the 3x3x3
+// stride-1 layers).  Why warp-level mma.sync (m16n8k16, bf16 -> fp32) here: the GEMM is M = (tap, ca) x N = cb x
 // K = voxels with ca, cb as small as 8.  tcgen05.mma needs M >= 64 with ONE uniform stride between its 8-row groups,
 // but the 8-channel groups of this M dimension are the taps, whose shared-memory offsets (dz*HY*HX + dy*HX + dx) are
-// not uniformly strided; padding M to 64 per tap costs 8x the tensor work.  m16n8k16 fits (2 taps x 8 ca) x 8 cb
-// exactly, and both operands come straight out of the natural [voxel][8 channels] layout with ldmatrix.trans.
+// not uniformly strided (wgrad_tc.cu side-steps that by letting tile ROWS carry the dy taps).  m16n8k16 fits
+// (2 taps x 8 ca) x 8 cb exactly, and both operands come straight out of the natural [voxel][8 channels] layout with
+// ldmatrix.trans, for any stride.
 //
 // One CTA stages a (TZ x TY x 16) tile of output positions plus its input halo with cp.async (double buffered,
 // 8-channel planes so every ldmatrix row is a 16 B contiguous chunk), each warp owns up to 16 (M-tile, N-block)
