@@ -257,6 +257,14 @@ WG_CASES = [
     (3, 1, 32, 8, False, (6, 8, 35)),
     (3, 1, 32, 32, False, (5, 7, 21)),
     (3, 1, 16, 16, False, (26, 9, 50)),
+    # tcgen05 stride-2 weight gradient (wgrad_tc_s2.cu): conv and transposed conv, every (planes, rows) plan
+    (4, 2, 8, 8, False, (22, 30, 38)),
+    (4, 2, 8, 16, False, (12, 20, 70)),
+    (4, 2, 16, 32, False, (10, 12, 14)),
+    (4, 2, 32, 8, False, (8, 10, 36)),
+    (4, 2, 8, 8, True, (9, 11, 19)),
+    (4, 2, 32, 32, True, (4, 5, 6)),
+    (4, 2, 8, 32, True, (7, 6, 17)),
 ]
 
 

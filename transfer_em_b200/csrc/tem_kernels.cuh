@@ -140,6 +140,10 @@ cudaError_t launch_wgrad_mma(const WgradArgs& a, cudaStream_t st);
 bool wgrad_tc_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);
 
+// wgrad_tc_s2.cu: tcgen05 weight gradient of the 4x4x4 stride-2 layers (parity classes = 2x2x2-tap stride-1 correlations)
+bool wgrad_tc_s2_supported(const WgradArgs& a);
+cudaError_t launch_wgrad_tc_s2(const WgradArgs& a, cudaStream_t st);
+
 // wgrad_tma.cu: TMA-staged, z-marching version of the tensor-core weight gradient
 bool wgrad_tma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tma(const WgradArgs& a, cudaStream_t st);

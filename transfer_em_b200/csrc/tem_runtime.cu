@@ -347,6 +347,7 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     // a kernel that cannot tile the shape (shared memory) answers cudaErrorInvalidConfiguration: the next one is tried
     cudaError_t e = cudaErrorInvalidConfiguration;
     if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) e = launch_wgrad_tc(a, st);
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_s2_supported(a)) e = launch_wgrad_tc_s2(a, st);
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) e = launch_wgrad_tma(a, st);
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) e = launch_wgrad_mma(a, st);
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) e = launch_wgrad_c1(a, st);
