@@ -124,6 +124,10 @@ size_t tc_s2_packed_bytes(const ConvArgs& a);
 cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 
+// conv_small.cu: strided 4x4x4 forward for small output volumes with K = 64*Cin (d4, d6)
+bool conv_small_supported(const ConvArgs& a);
+cudaError_t launch_conv_small(const ConvArgs& a, cudaStream_t st);
+
 // conv_mma.cu: mma.sync convolution for stride-2 / transposed / 1x1 layers with channel counts that are multiples of 8
 bool conv_mma_supported(const ConvArgs& a);
 cudaError_t launch_conv_mma(const ConvArgs& a, cudaStream_t st);

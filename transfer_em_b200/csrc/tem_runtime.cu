@@ -27,6 +27,7 @@ extern "C" const char* tem_last_error(void) { return g_err; }
 extern "C" int tem_abi_version(void) { return TEM_ABI_VERSION; }
 
 unsigned long long g_tem_launches = 0;
+const char* g_tem_last_kernel = "?";
 extern "C" uint64_t tem_launch_count(void) { return g_tem_launches; }
 
 static cudaEvent_t prof_event(Profiler& p) {
@@ -36,34 +37,34 @@ static cudaEvent_t prof_event(Profiler& p) {
 ProfScope::ProfScope(const tem_handle* hc, const char* layer, const char* op, double bytes, double flops, cudaStream_t s)
     : h(const_cast<tem_handle*>(hc)), st(s), idx(0), live(false) {
   if (!h || !h->prof.on) return;
-  ProfRec r; snprintf(r.tag, sizeof(r.tag), "%s.%s", layer, op);
+  ProfRec r; snprintf(r.tag, sizeof(r.tag), "%s.%s", layer, op); r.kernel = "?";
   r.e0 = prof_event(h->prof); r.e1 = prof_event(h->prof); r.bytes = bytes; r.flops = flops;
   cudaEventRecord(r.e0, st);
   idx = h->prof.recs.size(); h->prof.recs.push_back(r); live = true;
 }
-ProfScope::~ProfScope() { if (live) cudaEventRecord(h->prof.recs[idx].e1, st); }
+ProfScope::~ProfScope() { if (live) { cudaEventRecord(h->prof.recs[idx].e1, st); h->prof.recs[idx].kernel = g_tem_last_kernel; } }
 
 extern "C" int tem_profile_enable(tem_handle* h, int on) {
   if (!h) { tem_set_error("null handle"); return TEM_ERR_ARG; }
   h->prof.on = on != 0; h->prof.recs.clear(); h->prof.used = 0;
   return TEM_OK;
 }
-// text report, one line per tag: "tag count total_ms bytes_per_launch flops_per_launch"
+// text report, one line per tag: "tag count total_ms bytes_per_launch flops_per_launch kernel"
 extern "C" int tem_profile_report(tem_handle* h, char* buf, int64_t buflen) {
   if (!h || !buf || buflen < 1) { tem_set_error("bad arguments"); return TEM_ERR_ARG; }
   cudaDeviceSynchronize();
-  struct Agg { std::string tag; long n; double ms, bytes, flops; };
+  struct Agg { std::string tag; long n; double ms, bytes, flops; const char* kernel; };
   std::vector<Agg> aggs;
   for (auto& r : h->prof.recs) {
     float ms = 0.f; cudaEventElapsedTime(&ms, r.e0, r.e1);
     Agg* a = nullptr;
     for (auto& x : aggs) if (x.tag == r.tag) { a = &x; break; }
-    if (!a) { aggs.push_back({r.tag, 0, 0, 0, 0}); a = &aggs.back(); }
+    if (!a) { aggs.push_back({r.tag, 0, 0, 0, 0, r.kernel}); a = &aggs.back(); }
     a->n++; a->ms += ms; a->bytes += r.bytes; a->flops += r.flops;
   }
   int64_t off = 0; buf[0] = 0;
   for (auto& a : aggs) {
-    int w = snprintf(buf + off, (size_t)(buflen - off), "%s %ld %.6f %.1f %.1f\n", a.tag.c_str(), a.n, a.ms, a.bytes / a.n, a.flops / a.n);
+    int w = snprintf(buf + off, (size_t)(buflen - off), "%s %ld %.6f %.1f %.1f %s\n", a.tag.c_str(), a.n, a.ms, a.bytes / a.n, a.flops / a.n, a.kernel ? a.kernel : "?");
     if (w < 0 || off + w >= buflen) break;
     off += w;
   }
@@ -183,6 +184,7 @@ static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaS
   return kind == 2 ? tc_s2_pack_weights(a, dst, st) : (kind == 1 ? tc_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st));
 }
 static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
+  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? (a.form == 1 ? "conv_up_tc_kernel" : "conv_down_tc_kernel") : kind == 1 ? "conv3_tc_kernel" : "conv3_tc3_kernel";
   if (kind == 3) return launch_conv_tcw(a, wp, st);
   return kind == 2 ? launch_conv_tc_s2(a, wp, st) : (kind == 1 ? launch_conv_tc(a, wp, st) : launch_conv_tc3(a, wp, st));
 }
@@ -231,13 +233,16 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
     return TEM_OK;
   }
   static const bool no_c1 = getenv("TEM_NO_CONV_C1") != nullptr;     // debug knob
-  if (h->cfg.use_tensor_cores && !no_c1 && conv_c1_supported(a)) { TEM_CUDA(launch_conv_c1(a, st)); return TEM_OK; }
+  if (h->cfg.use_tensor_cores && !no_c1 && conv_c1_supported(a)) { g_tem_last_kernel = "conv_c1_kernel"; TEM_CUDA(launch_conv_c1(a, st)); return TEM_OK; }
+  static const bool no_small = getenv("TEM_NO_CONV_SMALL") != nullptr;   // debug knob
+  if (h->cfg.use_tensor_cores && !no_small && conv_small_supported(a)) { g_tem_last_kernel = "conv_small_s2_kernel"; TEM_CUDA(launch_conv_small(a, st)); return TEM_OK; }
   static const bool no_mma = getenv("TEM_NO_CONV_MMA") != nullptr;   // debug knob
   if (h->cfg.use_tensor_cores && !no_mma && conv_mma_supported(a)) {
     const cudaError_t e = launch_conv_mma(a, st);
-    if (e != cudaErrorInvalidConfiguration) { TEM_CUDA(e); return TEM_OK; }
+    if (e != cudaErrorInvalidConfiguration) { g_tem_last_kernel = "conv_mma_kernel"; TEM_CUDA(e); return TEM_OK; }
     (void)cudaGetLastError();                 // the shape does not tile into shared memory: direct kernel
   }
+  g_tem_last_kernel = "conv_direct_kernel";
   TEM_CUDA(launch_conv_direct(a, st));
   return TEM_OK;
 }
@@ -346,12 +351,12 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     static const bool no_wtc = getenv("TEM_NO_WGRAD_TC") != nullptr;   // debug knob: 3x3x3 weight gradients on the mma.sync kernel
     // a kernel that cannot tile the shape (shared memory) answers cudaErrorInvalidConfiguration: the next one is tried
     cudaError_t e = cudaErrorInvalidConfiguration;
-    if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) e = launch_wgrad_tc(a, st);
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_s2_supported(a)) e = launch_wgrad_tc_s2(a, st);
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) e = launch_wgrad_tma(a, st);
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) e = launch_wgrad_mma(a, st);
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) e = launch_wgrad_c1(a, st);
-    if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_wgrad_direct(a, st); }
+    if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) { e = launch_wgrad_tc(a, st); g_tem_last_kernel = "wgrad_tc_kernel"; }
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_s2_supported(a)) { e = launch_wgrad_tc_s2(a, st); g_tem_last_kernel = "wgrad_tc_s2_kernel"; }
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) { e = launch_wgrad_tma(a, st); g_tem_last_kernel = "wgrad_tma_kernel"; }
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) { e = launch_wgrad_mma(a, st); g_tem_last_kernel = "wgrad_mma_kernel"; }
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) { e = launch_wgrad_c1(a, st); g_tem_last_kernel = "wgrad_c1_kernel"; }
+    if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_wgrad_direct(a, st); g_tem_last_kernel = "wgrad_direct_kernel"; }
     TEM_CUDA(e);
   }
   return TEM_OK;

@@ -56,7 +56,8 @@ struct DiscPass {
 struct NcclApi;
 
 // optional per-launch CUDA-event timing, aggregated by (layer, op) tag: used by bench.py for the roofline line
-struct ProfRec { char tag[24]; cudaEvent_t e0, e1; double bytes, flops; };
+struct ProfRec { char tag[24]; const char* kernel; cudaEvent_t e0, e1; double bytes, flops; };
+extern const char* g_tem_last_kernel;   // name of the kernel the last dispatch chose (profiling only)
 struct Profiler {
   bool on = false;
   std::vector<ProfRec> recs;

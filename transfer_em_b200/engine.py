@@ -249,13 +249,13 @@ class Engine:
         check(self._lib.tem_profile_enable(self._h, 1 if on else 0))
 
     def profile_report(self):
-        """{tag: dict(count, ms, bytes, flops)} - per-launch algorithmic bytes / flops, total ms."""
+        """{tag: dict(count, ms, bytes, flops, kernel)} - per-launch algorithmic bytes / flops, total ms, kernel chosen."""
         buf = C.create_string_buffer(1 << 16)
         check(self._lib.tem_profile_report(self._h, buf, len(buf)))
         out = {}
         for line in buf.value.decode().splitlines():
-            t, n, ms, by, fl = line.split()
-            out[t] = dict(count=int(n), ms=float(ms), bytes=float(by), flops=float(fl))
+            t, n, ms, by, fl, kn = line.split()
+            out[t] = dict(count=int(n), ms=float(ms), bytes=float(by), flops=float(fl), kernel=kn)
         return out
 
     # ---- data parallel ----------------------------------------------------------------------
