@@ -259,7 +259,7 @@ bool tcw_conv_supported(const ConvArgs& a) {
   for (int i = 0; i < 3; ++i) if (a.k[i] != 3 || a.stride[i] != 1 || a.conv_off[i]) return false;
   if (a.s0.dtype != DT_BF16 || a.out_dtype != DT_BF16 || a.s0.origins || a.use_lut || a.bias) return false;
   const int cin = a.C0 + a.C1;
-  if (cin < 64 || a.C0 % WCH || a.C1 % WCH) return false;
+  if (cin < WCH || a.C0 % WCH || a.C1 % WCH) return false;
   if (a.s0.C != a.C0 || a.s0.coff != 0) return false;
   if (a.C1 && (a.s1.dtype != DT_BF16 || a.s1.C != a.C1 || a.s1.coff != 0)) return false;
   if (a.Cout % 8 || a.Cout < 32 || a.out_C % 8 || a.out_coff % 8) return false;
