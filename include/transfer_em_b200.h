@@ -150,6 +150,17 @@ int tem_standardize_u8(const uint8_t* in, float* out, int64_t n, const float mea
 /* utils.py:109,118: (y*std+mean+1)*127.5 -> rint -> wrap to uint8 */
 int tem_unstandardize_to_u8(const float* in, uint8_t* out, int64_t n, const float meanstd[2], void* stream);
 
+/* ---- input conditioning on device ---- */
+/* datasets.py:123-155 augment(): per sample, output axis k walks input axis perm[k] (tf.transpose), flipped output axes are
+   reversed (tf.reverse), then `*= var_adj; += mean_adj` (two fp32 roundings, as in the reference).  in_dtype TEM_U8 fuses
+   scale_tensor + standardize_population (meanstd) in front, TEM_F32 takes the already standardised tensor.  All pointers are
+   device pointers: in [B, *], out fp32 [B, n0, n1, n2(, 1)], perm / flip int32 [B][3], var_adj / mean_adj fp32 [B]. */
+int tem_augment(const void* in, int in_dtype, const float meanstd[2], float* out, int32_t B, const int32_t out_dims[3],
+                const int32_t* perm, const int32_t* flip, const float* var_adj, const float* mean_adj, void* stream);
+/* datasets.py:173-190 get_meanstd(), one tensor: out[0] = tf.math.reduce_mean, out[1] = tf.math.reduce_variance (population).
+   scratch: 32 zeroed bytes of device memory, left zeroed. */
+int tem_mean_var(const float* in, int64_t n, void* scratch, float* out, void* stream);
+
 /* ---- per-op entry points (tests, layer-level parity) ---- */
 typedef struct {
   /* geometry */

@@ -665,6 +665,19 @@ def predict_ng_cube_oracle(volume_zyx: np.ndarray, start, size, predict_fn, mean
     return out_buffer[0:size[2], 0:size[1], 0:size[0]]
 
 
+def augment(t: np.ndarray, perm, flip, var_adj, mean_adj) -> np.ndarray:
+    """datasets.py:123-155 with the random choices made explicit: t [*spatial, 1] float32 -> transpose(perm + [channel]) ->
+    reverse the flipped axes -> *= var_adj -> += mean_adj (two float32 roundings)."""
+    nd = t.ndim - 1
+    out = np.transpose(t, tuple(perm) + (nd,))
+    for d in range(nd):
+        if flip[d]:
+            out = np.flip(out, axis=d)
+    out = out.astype(np.float32) * np.float32(var_adj)
+    out = out + np.float32(mean_adj)
+    return np.ascontiguousarray(out.astype(np.float32))
+
+
 def get_meanstd(tensors: Sequence[np.ndarray]):
     """datasets.py:173-190: mean of per-tensor means, sqrt of mean of per-tensor variances."""
     mean = np.float32(0); var = np.float32(0)

@@ -401,3 +401,46 @@ def test_tma_wgrad_variant_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "tensor_core_wgrad", "-x"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_device_augment_bit_exact():
+    """datasets.py:123-155 on device: axis shuffle + flips are index work (bit-exact), the intensity jitter is two fp32
+    roundings in the reference's order; the uint8 entry fuses scale_tensor + standardize_population in front."""
+    from transfer_em_b200 import datasets as D
+    r = np.random.default_rng(42)
+    B, n = 5, 12
+    ms = (0.04, 0.57)
+    u = r.integers(0, 256, (B, n, n, n), dtype=np.uint8)
+    choices = D.draw_augmentation(B, 3, r)
+    perm, flip, var, mean = choices
+    assert sorted(perm[0].tolist()) == [0, 1, 2] and var.min() >= 1.0 and var.max() <= 1.05 and abs(mean).max() <= 0.05
+    out = D.augment(u, meanstd=ms, choices=choices)
+    assert out.shape == (B, n, n, n, 1) and out.dtype == np.float32
+    for b in range(B):
+        xs = O.standardize_population(O.scale_tensor(u[b]), ms)          # [n,n,n,1] float32
+        ref = O.augment(xs, perm[b], flip[b], var[b], mean[b])
+        assert np.array_equal(out[b], ref), b
+    # float32 entry, non-cubic patch with one shared permutation, and the 2-D form
+    x = r.standard_normal((3, 4, 6, 5, 1)).astype(np.float32)
+    pm = np.tile(np.array([[1, 2, 0]], np.int32), (3, 1)); fl = np.array([[0, 1, 1], [1, 0, 0], [1, 1, 1]], np.int32)
+    va = np.array([1.0, 1.02, 1.05], np.float32); me = np.array([0.05, -0.05, 0.0], np.float32)
+    out = D.augment(x, choices=(pm, fl, va, me))
+    for b in range(3):
+        assert np.array_equal(out[b], O.augment(x[b], pm[b], fl[b], va[b], me[b]))
+    x2 = r.standard_normal((2, 7, 9)).astype(np.float32)
+    pm2 = np.array([[0, 2, 1], [0, 2, 1]], np.int32); fl2 = np.array([[0, 1, 0], [0, 0, 1]], np.int32)
+    out2 = D.augment(x2, choices=(pm2, fl2, va[:2], me[:2]))
+    for b in range(2):
+        assert np.array_equal(out2[b], O.augment(x2[b][..., None], pm2[b, 1:] - 1, fl2[b, 1:], va[b], me[b]))
+
+
+def test_device_get_meanstd():
+    """datasets.py:173-190: mean of per-tensor means, sqrt of the mean of per-tensor population variances."""
+    from transfer_em_b200 import datasets as D
+    r = np.random.default_rng(43)
+    ts = [(r.standard_normal((20, 31, 17, 1)) * (0.5 + i) + 0.1 * i).astype(np.float32) for i in range(4)]
+    m, s = D.get_meanstd(ts)
+    mr, sr = O.get_meanstd(ts)
+    m64 = np.mean([t.astype(np.float64).mean() for t in ts]); s64 = np.sqrt(np.mean([t.astype(np.float64).var() for t in ts]))
+    assert abs(m - m64) < 2e-6 * max(1.0, abs(m64)) and abs(s - s64) < 2e-6 * s64
+    assert abs(m - mr) < 1e-5 and abs(s - sr) < 1e-5 * sr

@@ -156,3 +156,23 @@ def test_tiling_plan_and_stitch():
     assert np.array_equal(out, vol[19:19 + 36, 19:19 + 40, 19:19 + 72])
     # fetch_input truncates instead of rounding (utils.py:123-125): may differ by one
     assert np.max(np.abs(inb.astype(int) - out.astype(int))) <= 1
+
+
+def test_augment_oracle_matches_explicit_loops():
+    """datasets.py:123-155: transpose(perm) -> reverse(flipped axes) -> *= var -> += mean, written out voxel by voxel."""
+    from oracle import tem_oracle as O
+    r = np.random.default_rng(11)
+    t = r.standard_normal((4, 5, 6, 1)).astype(np.float32)
+    perm, flip, var, mean = (2, 0, 1), (1, 0, 1), np.float32(1.03), np.float32(-0.02)
+    out = O.augment(t, perm, flip, var, mean)
+    assert out.shape == (6, 4, 5, 1) and out.dtype == np.float32
+    for i0 in range(6):
+        for i1 in range(4):
+            for i2 in range(5):
+                o = [i0, i1, i2]
+                o = [o[k] if not flip[k] else out.shape[k] - 1 - o[k] for k in range(3)]
+                src = [0, 0, 0]
+                for k in range(3):
+                    src[perm[k]] = o[k]
+                ref = np.float32(np.float32(t[src[0], src[1], src[2], 0] * var) + mean)
+                assert out[i0, i1, i2, 0] == ref

@@ -24,7 +24,7 @@ constexpr int TX = 8, TY = 16, HX = TX + 2, HY = TY + 2;
 constexpr int PLANE_BYTES = HY * HX * 16;
 constexpr int PLANE_STRIDE = 2944;
 constexpr int RING3_MAX = 16;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;     // TMA producer, MMA issuer, 2 x 4 epilogue warps (two per TMEM lane quadrant, alternating output slices)
 constexpr int kMaxChunk = 64;
 
 struct Tc3Args {
@@ -50,7 +50,7 @@ __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
 }
 
 template <int CP>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
   constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -167,11 +167,14 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int oy = y0 + yl, ox = x0 + xl;
     const bool inside = oy < a.L[1] && ox < a.L[2];
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    // zero the accumulator strip (this warp's 32 lanes, all allocated columns)
-    for (int c = 0; c < a.tmem_cols; c += 8) tmem_st8_zero(lane_base + (uint32_t)c);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    mbar_arrive(&tzero_bar);
+    const int ew = (warp - 2) >> 2;                 // 0 / 1: this warp drains the even / odd output slices of its quadrant
+    if (ew == 0) {
+      // zero the accumulator strip (this quadrant's 32 lanes, all allocated columns)
+      for (int c = 0; c < a.tmem_cols; c += 8) tmem_st8_zero(lane_base + (uint32_t)c);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tzero_bar);
+    }
     const bool has_c8[4] = {0 < a.Cout, 8 < a.Cout, 16 < a.Cout, 24 < a.Cout};
     // Operands of the fused epilogue (stored activation of the LeakyReLU' factor) are fetched PF output slices ahead of
     // their use: with one 16 B load per thread and slice in flight an SM keeps only ~4 KB of this stream outstanding,
@@ -187,11 +190,11 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       }
     };
 #pragma unroll
-    for (int u = 0; u < PF; ++u) fetch_ref(u, refq[u]);
-    for (int zb = 0; zb < nz; zb += PF) {
+    for (int u = 0; u < PF; ++u) fetch_ref(2 * u + ew, refq[u]);
+    for (int zb = 0; zb < nz; zb += 2 * PF) {
 #pragma unroll
     for (int pu = 0; pu < PF; ++pu) {
-      const int zo = zb + pu;
+      const int zo = zb + 2 * pu + ew;
       if (zo >= nz) break;
       const int oz = z0 + zo;
       mbar_wait(&tfull_bar[zo], 0);
@@ -216,7 +219,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           }
         }
       }
-      fetch_ref(zo + PF, refq[pu]);
+      fetch_ref(zo + 2 * PF, refq[pu]);
       if (a.drop_key) {
         const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
 #pragma unroll

@@ -228,6 +228,74 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
   adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale); ++g_tem_launches;
   return cudaGetLastError();
 }
+// ---- input conditioning on device (datasets.py:123-155 augment, :173-190 get_meanstd) ----
+// augment: tf.transpose(perm) -> tf.reverse on the flipped axes -> *= var_adj -> += mean_adj, per sample; with a uint8
+// source the scale_tensor + standardize_population steps that precede it in the reference pipeline are fused in front.
+__global__ void augment_kernel(const AugmentArgs a) {
+  const long long per = (long long)a.n[0] * a.n[1] * a.n[2];
+  const long long total = per * a.B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per); long long r = i % per;
+    int o[3];
+    o[2] = (int)(r % a.n[2]); r /= a.n[2]; o[1] = (int)(r % a.n[1]); o[0] = (int)(r / a.n[1]);
+    // output axis k walks input axis perm[k]; a flipped output axis is read backwards
+    int src[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int pk = a.perm[b * 3 + k];
+      src[pk] = a.flip[b * 3 + k] ? a.n[k] - 1 - o[k] : o[k];
+    }
+    // input dims: in_n[perm[k]] = n[k]
+    int in_n[3] = {1, 1, 1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) in_n[a.perm[b * 3 + k]] = a.n[k];
+    const long long si = (long long)b * per + ((long long)src[0] * in_n[1] + src[1]) * in_n[2] + src[2];
+    float v;
+    if (a.in_dtype == DT_U8) v = tem_standardize((float)reinterpret_cast<const uint8_t*>(a.in)[si], a.mean, a.stdv);
+    else v = reinterpret_cast<const float*>(a.in)[si];
+    v = __fmul_rn(v, a.var_adj[b]);
+    v = __fadd_rn(v, a.mean_adj[b]);
+    a.out[i] = v;
+  }
+}
+cudaError_t launch_augment(const AugmentArgs& a, cudaStream_t st) {
+  const long long total = (long long)a.B * a.n[0] * a.n[1] * a.n[2];
+  if (total == 0) return cudaSuccess;
+  augment_kernel<<<grid_for(total), 256, 0, st>>>(a); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
+// tf.math.reduce_mean / reduce_variance of one fp32 tensor: fp64 sum and sum of squares, one atomic pair per block,
+// finalised by the last block (out = {mean, population variance} as fp32)
+__global__ void mean_var_kernel(const float* x, long long n, double* acc, unsigned int* done, float* out) {
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)x[i]; s += v; q += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  __shared__ double ss[8], sq[8];
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += ss[w]; tq += sq[w]; }
+    atomicAdd(&acc[0], ts); atomicAdd(&acc[1], tq);
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      const double S = atomicAdd(&acc[0], 0.0), Q = atomicAdd(&acc[1], 0.0);
+      const double m = S / (double)n;
+      out[0] = (float)m; out[1] = (float)fmax(Q / (double)n - m * m, 0.0);
+      acc[0] = 0.0; acc[1] = 0.0; *done = 0u;      // scratch is reusable by the next call on the stream
+    }
+  }
+}
+cudaError_t launch_mean_var(const float* x, long long n, double* scratch, float* out, cudaStream_t st) {
+  unsigned int* done = reinterpret_cast<unsigned int*>(scratch + 2);
+  int grid = (int)((n + 256 * 8 - 1) / (256 * 8)); if (grid < 1) grid = 1; if (grid > 148 * 8) grid = 148 * 8;
+  mean_var_kernel<<<grid, 256, 0, st>>>(x, n, scratch, done, out); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_standardize_u8(const uint8_t* in, float* out, long long n, float mean, float stdv, cudaStream_t st) {
   standardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv); ++g_tem_launches;
   return cudaGetLastError();

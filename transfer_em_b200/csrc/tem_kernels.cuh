@@ -178,6 +178,17 @@ cudaError_t launch_dropout_mask(uint32_t key, float* out, long long n, cudaStrea
 cudaError_t launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t st);
 cudaError_t launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
 cudaError_t launch_init_normal(float* p, long long n, uint64_t seed, float stdv, cudaStream_t st);
+struct AugmentArgs {     // datasets.py:123-155
+  const void* in; int in_dtype;     // DT_U8 (scale + standardise fused in front) or DT_F32
+  float* out;
+  int B, n[3];                      // OUTPUT dims (z,y,x); 2-D data has n[0] = 1 and perm[0] = 0
+  const int* perm;                  // device [B][3]: output axis k <- input axis perm[k]
+  const int* flip;                  // device [B][3]
+  const float* var_adj; const float* mean_adj;   // device [B]
+  float mean, stdv;                 // standardisation of a uint8 source
+};
+cudaError_t launch_augment(const AugmentArgs& a, cudaStream_t st);
+cudaError_t launch_mean_var(const float* x, long long n, double* scratch /* 2 doubles + 1 uint, zeroed */, float* out, cudaStream_t st);
 struct StitchArgs {
   const float* y;      // generator output fp32 [T, od+2*tpad, .., 1]
   const int* index;    // [T][3] (x,y,z) output index of each tile (utils.py:84)

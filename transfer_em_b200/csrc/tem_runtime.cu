@@ -1107,6 +1107,24 @@ extern "C" int tem_unstandardize_to_u8(const float* in, uint8_t* out, int64_t n,
   TEM_CUDA(launch_unstandardize_u8(in, out, n, ms[0], ms[1], (cudaStream_t)stream));
   return TEM_OK;
 }
+extern "C" int tem_augment(const void* in, int in_dtype, const float meanstd[2], float* out, int32_t B, const int32_t out_dims[3],
+                           const int32_t* perm, const int32_t* flip, const float* var_adj, const float* mean_adj, void* stream) {
+  if (!in || !out || !out_dims || !perm || !flip || !var_adj || !mean_adj || B < 0) ARG_FAIL("tem_augment: bad arguments");
+  if (in_dtype != DT_U8 && in_dtype != DT_F32) ARG_FAIL("tem_augment: input must be uint8 or float32");
+  if (in_dtype == DT_U8 && !meanstd) ARG_FAIL("uint8 input needs meanstd");
+  AugmentArgs a; memset(&a, 0, sizeof(a));
+  a.in = in; a.in_dtype = in_dtype; a.out = out; a.B = B;
+  for (int i = 0; i < 3; ++i) { if (out_dims[i] < 1) ARG_FAIL("bad dims"); a.n[i] = out_dims[i]; }
+  a.perm = perm; a.flip = flip; a.var_adj = var_adj; a.mean_adj = mean_adj;
+  a.mean = meanstd ? meanstd[0] : 0.f; a.stdv = meanstd ? meanstd[1] : 1.f;
+  TEM_CUDA(launch_augment(a, (cudaStream_t)stream));
+  return TEM_OK;
+}
+extern "C" int tem_mean_var(const float* in, int64_t n, void* scratch, float* out, void* stream) {
+  if (!in || !scratch || !out || n < 1) ARG_FAIL("tem_mean_var: bad arguments");
+  TEM_CUDA(launch_mean_var(in, n, (double*)scratch, out, (cudaStream_t)stream));
+  return TEM_OK;
+}
 extern "C" int tem_focal_logits(const float* logits, int64_t n, float target, float gamma, float scale,
                                 float* loss_out, float* grad, void* stream) {
   if (!logits || n <= 0) ARG_FAIL("bad arguments");

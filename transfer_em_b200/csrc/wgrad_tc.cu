@@ -250,8 +250,10 @@ bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
   int cols = 32; while (cols < 9 * t.N) cols <<= 1;
   t.tmem_cols = cols;
   // rings as deep as ~150 KB allow (one CTA per SM anyway: the accumulators take most of TMEM)
+  static const char* ring_s = getenv("TEM_WTC_RING");    // debug knob: cap of the x ring depth
+  const int xr_cap = ring_s ? atoi(ring_s) : XR_MAX;
   t.XR = 3; t.DR = 5;
-  while (t.XR < XR_MAX && (size_t)(t.XR + 1) * t.xa_bytes + (size_t)(t.DR + 1) * t.gb_bytes <= 150 * 1024) { ++t.XR; ++t.DR; }
+  while (t.XR < xr_cap && t.XR < XR_MAX && (size_t)(t.XR + 1) * t.xa_bytes + (size_t)(t.DR + 1) * t.gb_bytes <= 150 * 1024) { ++t.XR; ++t.DR; }
   smem = (size_t)t.XR * t.xa_bytes + (size_t)t.DR * t.gb_bytes + 1024;
   const size_t red = (size_t)27 * w.Ca * w.Cb * 4;
   if (red + 1024 > smem) smem = red + 1024;
