@@ -38,7 +38,8 @@ def _tt(P, k):
     return [torch.tensor(p, dtype=torch.float32) for p in P[k]]
 
 
-@pytest.mark.parametrize("is3d,wf,n,B", [(True, 8, 74, 2), (True, 8, 78, 1), (False, 8, 74, 3), (True, 4, 74, 1), (True, 16, 74, 1)])
+@pytest.mark.parametrize("is3d,wf,n,B", [(True, 8, 74, 2), (True, 8, 78, 1), (False, 8, 74, 3), (True, 4, 74, 1), (True, 16, 74, 1),
+                                          (True, 2, 74, 1)])   # wf=2: wide tcgen05 kernel incl. its two-source (crop-and-concat) passes
 def test_generator_forward(is3d, wf, n, B):
     # weights 5x the init scale so that activations are O(0.1..1) and the comparison is meaningful
     P = _params(wf, is3d, 11, scale=5.0)

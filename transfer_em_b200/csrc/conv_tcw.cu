@@ -162,14 +162,25 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     mbar_arrive(&tzero_bar);
     const int co0 = cg * CPW;
     const int ncol = min(CPW, a.Cout - co0);
-    for (int zo = 0; zo < nz; ++zo) {
-      const int oz = z0 + zo;
-      uint4 refq[CPW / 8];
-      if (a.ref && inside) {
-        const long long ro = ((((long long)b * a.RZ + oz + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff + co0;
+    // the LeakyReLU' operand of the data gradient is fetched PF output slices ahead (see conv_tc3.cu)
+    constexpr int PF = 3;
+    uint4 refq[PF][CPW / 8];
+    const long long ref_zstride = (long long)a.RY * a.RX * a.ref_C;
+    const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff + co0;
+    auto fetch_ref = [&](int zo, uint4* q) {
+      if (a.ref && inside && zo < nz) {
 #pragma unroll
-        for (int c = 0; c < CPW / 8; ++c) if (c * 8 < ncol) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ro + c * 8));
+        for (int c = 0; c < CPW / 8; ++c) if (c * 8 < ncol) q[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ref_base + (long long)zo * ref_zstride + c * 8));
       }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) fetch_ref(u, refq[u]);
+    for (int zb = 0; zb < nz; zb += PF) {
+#pragma unroll
+    for (int pu = 0; pu < PF; ++pu) {
+      const int zo = zb + pu;
+      if (zo >= nz) break;
+      const int oz = z0 + zo;
       mbar_wait(&tfull_bar[zo], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[CPW];
@@ -188,7 +199,7 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c + u]);
           if (a.ref) {
             float f[8];
-            unpack8(refq[c / 8], f);
+            unpack8(refq[pu][c / 8], f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
           }
@@ -212,6 +223,8 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           *reinterpret_cast<uint4*>(op + c) = pk;
         }
       }
+      fetch_ref(zo + PF, refq[pu]);
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
