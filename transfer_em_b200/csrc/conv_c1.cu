@@ -6,6 +6,7 @@
 // LUT, fp32/bf16 fakes get their virtual zero padding, tiles may come from per-sample origins in one volume), every
 // thread then produces 4 z-consecutive voxels with a register sliding window: FMA-bound inner loop, 16 B coalesced
 // stores, fused LeakyReLU / LeakyReLU' * dropout epilogues.
+#include <stdlib.h>
 #include <string.h>
 #include "tem_kernels.cuh"
 
@@ -194,6 +195,148 @@ __global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second-generation 1 -> 8 forward (g0 / d0, incl. the uint8 LUT entry and per-tile origins of tiled inference):
+//   * 128 threads own a 24 x 16 x 4 output tile, every thread 3 x-positions (x, x+8, x+16: the 8 lanes of a row still
+//     write 128 B contiguous) x 4 z = 96 accumulators, so one broadcast weight load (2 x LDS.128) feeds 12 FFMA x 8 and
+//     the index arithmetic is amortised over 12 outputs instead of 4;
+//   * CTAs are persistent over tiles: LUT and weights are staged once, the halo of the next tile is fetched into
+//     registers while the current one is computed.
+// ------------------------------------------------------------------------------------------------
+constexpr int W2_TX = 24, W2_TY = 16, W2_TZ = 4, W2_NT = 128, W2_V = 3;
+constexpr int W2_HX = W2_TX + 2, W2_HY = W2_TY + 2, W2_HZ = W2_TZ + 2, W2_HALO = W2_HZ * W2_HY * W2_HX;
+constexpr int W2_NS = (W2_HALO + W2_NT - 1) / W2_NT;
+
+template <int SDT>
+__device__ __forceinline__ void w2_fetch(const ConvArgs& a, long long tl, int ntx, int nty, int ntz, int tid, float* raw) {
+  long long t = tl;
+  const int tx = (int)(t % ntx); t /= ntx;
+  const int ty = (int)(t % nty); t /= nty;
+  const int tz = (int)(t % ntz); t /= ntz;
+  const int b = (int)t;
+  const SrcView& S = a.s0;
+  int oz = 0, oy = 0, ox = 0; long long sbase = (long long)b * S.bstride;
+  if (S.origins) { oz = S.origins[b * 3]; oy = S.origins[b * 3 + 1]; ox = S.origins[b * 3 + 2]; sbase = 0; }
+  const int zb = tz * W2_TZ + S.shift[0] + oz, yb = ty * W2_TY + S.shift[1] + oy, xb = tx * W2_TX + S.shift[2] + ox;
+#pragma unroll
+  for (int sI = 0; sI < W2_NS; ++sI) {
+    const int i = tid + sI * W2_NT;
+    const int hx = i % W2_HX, r = i / W2_HX, hy = r % W2_HY, hz = r / W2_HY;
+    const int z = zb + hz, y = yb + hy, x = xb + hx;
+    const bool ok = i < W2_HALO && z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X;
+    const long long off = sbase + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff;
+    float v = (SDT == DT_U8) ? -1.f : 0.f;           // u8: < 0 marks "outside"
+    if (ok) {
+      if (SDT == DT_U8) v = (float)reinterpret_cast<const uint8_t*>(S.p)[off];
+      else if (SDT == DT_BF16) v = bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
+      else v = reinterpret_cast<const float*>(S.p)[off];
+    }
+    raw[sI] = v;
+  }
+}
+
+template <int SDT>
+__global__ void __launch_bounds__(W2_NT, 3) conv_c1in_v2_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz,
+                                                                const long long ntiles, const long long tiles_per_cta) {
+  __shared__ float lut[256];
+  __shared__ float tile[W2_HALO];
+  __shared__ __align__(16) float wsm[27 * 8];
+  const int tid = threadIdx.x;
+  if (SDT == DT_U8) for (int i = tid; i < 256; i += W2_NT) lut[i] = tem_standardize((float)i, a.lut_mean, a.lut_std);
+  for (int i = tid; i < 27 * 8; i += W2_NT) {
+    const int co = i & 7, tap = i >> 3;
+    wsm[i] = (co < a.Cout) ? bf2f(__float2bfloat16_rn(a.w[tap * a.ws_tap + (long long)co * a.ws_out])) : 0.f;
+  }
+  const float fill = (SDT == DT_U8 && a.s0.origins) ? tem_standardize(0.f, a.lut_mean, a.lut_std) : 0.f;   // as the first-generation kernel
+  const int lx = tid & 7, ly = tid >> 3;
+  const long long t0 = (long long)blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
+  float raw[W2_NS];
+  if (t0 < t1) w2_fetch<SDT>(a, t0, ntx, nty, ntz, tid, raw);
+  for (long long tl = t0; tl < t1; ++tl) {
+    __syncthreads();
+#pragma unroll
+    for (int sI = 0; sI < W2_NS; ++sI) {
+      const int i = tid + sI * W2_NT;
+      if (i < W2_HALO) tile[i] = (SDT == DT_U8) ? (raw[sI] < 0.f ? fill : lut[(int)raw[sI]]) : raw[sI];
+    }
+    __syncthreads();
+    if (tl + 1 < t1) w2_fetch<SDT>(a, tl + 1, ntx, nty, ntz, tid, raw);
+    float acc[W2_V][W2_TZ][8];
+#pragma unroll
+    for (int v = 0; v < W2_V; ++v)
+#pragma unroll
+      for (int j = 0; j < W2_TZ; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[v][j][c] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        float col[W2_V][W2_HZ];
+#pragma unroll
+        for (int v = 0; v < W2_V; ++v)
+#pragma unroll
+          for (int hz = 0; hz < W2_HZ; ++hz) col[v][hz] = tile[(hz * W2_HY + ly + dy) * W2_HX + lx + 8 * v + dx];
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8 + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int v = 0; v < W2_V; ++v)
+#pragma unroll
+            for (int j = 0; j < W2_TZ; ++j)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[v][j][c] = fmaf(col[v][j + dz], wv[c], acc[v][j][c]);
+        }
+      }
+    long long t = tl;
+    const int tx = (int)(t % ntx); t /= ntx;
+    const int ty = (int)(t % nty); t /= nty;
+    const int tz = (int)(t % ntz); t /= ntz;
+    const int b = (int)t;
+    const int oy_ = ty * W2_TY + ly;
+    if (oy_ < a.L[1]) {
+#pragma unroll
+      for (int v = 0; v < W2_V; ++v) {
+        const int ox_ = tx * W2_TX + lx + 8 * v;
+        if (ox_ >= a.L[2]) continue;
+#pragma unroll
+        for (int j = 0; j < W2_TZ; ++j) {
+          const int oz_ = tz * W2_TZ + j;
+          if (oz_ >= a.L[0]) break;
+          float o[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { o[u] = acc[v][j][u]; if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope; }
+          uint4 pk; pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+          bf16* op = reinterpret_cast<bf16*>(a.out) + ((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff;
+          *reinterpret_cast<uint4*>(op) = pk;
+        }
+      }
+    }
+  }
+}
+
+static bool c1in_v2_ok(const ConvArgs& a) {
+  static const bool off = getenv("TEM_CONV_C1_V1") != nullptr;      // debug knob: first-generation kernel
+  return !off && a.form == 0 && a.C0 == 1 && a.Cout == 8 && !a.ref && !a.drop_key && !a.accumulate && !a.bias &&
+         (a.use_lut ? a.s0.dtype == DT_U8 : a.s0.dtype != DT_U8);
+}
+static cudaError_t launch_c1in_v2(const ConvArgs& a, cudaStream_t st) {
+  const int ntx = (a.L[2] + W2_TX - 1) / W2_TX, nty = (a.L[1] + W2_TY - 1) / W2_TY, ntz = (a.L[0] + W2_TZ - 1) / W2_TZ;
+  const long long ntiles = (long long)a.B * ntx * nty * ntz;
+  if (ntiles == 0) return cudaSuccess;
+  long long gx = 148 * 3;
+  if (gx > ntiles) gx = ntiles;
+  const long long per = (ntiles + gx - 1) / gx;
+  gx = (ntiles + per - 1) / per;
+  if (a.s0.dtype == DT_U8) conv_c1in_v2_kernel<DT_U8><<<(unsigned)gx, W2_NT, 0, st>>>(a, ntx, nty, ntz, ntiles, per);
+  else if (a.s0.dtype == DT_BF16) conv_c1in_v2_kernel<DT_BF16><<<(unsigned)gx, W2_NT, 0, st>>>(a, ntx, nty, ntz, ntiles, per);
+  else conv_c1in_v2_kernel<DT_F32><<<(unsigned)gx, W2_NT, 0, st>>>(a, ntx, nty, ntz, ntiles, per);
+  ++g_tem_launches;
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 bool conv_c1_supported(const ConvArgs& a) {
@@ -212,6 +355,7 @@ cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st) {
   const int ntx = (a.L[2] + TXT - 1) / TXT, nty = (a.L[1] + TY - 1) / TY, ntz = (a.L[0] + TZ - 1) / TZ;
   const long long grid = (long long)a.B * ntx * nty * ntz;
   if (grid == 0) return cudaSuccess;
+  if (c1in_v2_ok(a)) return launch_c1in_v2(a, st);
   if (a.C0 == 1) {
     if (a.Cout == 8) conv_c1in_kernel<8><<<(unsigned)grid, 256, 0, st>>>(a, ntx, nty, ntz, a.form == 1);
     else conv_c1in_kernel<16><<<(unsigned)grid, 256, 0, st>>>(a, ntx, nty, ntz, a.form == 1);
