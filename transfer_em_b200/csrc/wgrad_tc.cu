@@ -239,10 +239,12 @@ bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
   t.M = (t.pa == 4) ? 128 : 64;
   t.RA = (t.M / 8) / t.pa;
   int rb = t.RA - 2;
-  while (rb > 1 && rb * w.Cb > 56) --rb;
+  static const char* nmax_s = getenv("TEM_WTC_NMAX");     // debug knob: 28 keeps the 9 accumulators within 256 TMEM columns
+  const int nmax = nmax_s ? atoi(nmax_s) : 56;
+  while (rb > 1 && rb * w.Cb > nmax) --rb;
   if (t.M == 128) while (rb > 1 && (rb * w.Cb) % 16) --rb;
   t.RB = rb; t.N = rb * w.Cb;
-  if (t.N > 56 || (t.M == 128 && t.N % 16)) return false;
+  if (t.N > 56 || (t.M == 128 && t.N % 16)) return false;   // Cb = 32 keeps N = 32 even under a smaller cap
   t.NR = (w.L[2] + 2 + 15) / 16;
   t.WA = 16 * t.NR; t.WB = 16 * t.NR + 8;
   if (t.WB > 256) return false;
