@@ -278,12 +278,18 @@ def main():
     per_launch_ms = t["ms"] / t["count"]
     ach_gbs = t["bytes"] / (t["ms"] * 1e-3) / 1e9
     ach_tf = t["flops"] / (t["ms"] * 1e-3) / 1e12
-    traffic = None
+    # DRAM traffic comes from the committed ncu capture of this kernel on its largest captured layer (one launch), set
+    # beside the algorithmic bytes of that same launch
+    traffic, traffic_of = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(tname, {}).get("dram_bytes_per_launch")
+        caps = [c for c in json.load(open(tp)).get(tname, {}).get("captures", []) if c.get("tag") in rep]
+        if caps:
+            c = max(caps, key=lambda c: rep[c["tag"]]["bytes"])
+            traffic = c["dram_bytes_per_launch"]
+            traffic_of = {"layer": c["tag"], "algorithmic_bytes": rep[c["tag"]]["bytes"], "capture": "profiles/ncu_r1_" + c["capture"] + ".txt"}
     roofline = {"kernel": tname, "bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
-                "traffic": traffic, "peak_source": pk_src, "avg_launch_ms": per_launch_ms, "launches_per_step": t["count"] / PK,
+                "traffic": traffic, "traffic_of": traffic_of, "peak_source": pk_src, "avg_launch_ms": per_launch_ms, "launches_per_step": t["count"] / PK,
                 "share_of_conv_time": t["ms"] / tot_ms, "achieved_tflops": ach_tf,
                 "algorithmic_bytes_per_launch": t["bytes"] / t["count"], "flops_per_launch": t["flops"] / t["count"],
                 "layers": sorted(t["tags"]),

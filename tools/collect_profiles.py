@@ -26,7 +26,8 @@ for f in sorted(os.listdir(SRC)):
         return float(mm.group(1).replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(mm.group(2), 1)
     dur = re.search(r"gpu__time_duration.sum\s+([0-9.,]+) (\w+)", txt)
     if kn:
-        traffic.setdefault(kn.group(1), []).append({"capture": m.group(1), "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+        parts = m.group(1).split("_")
+        traffic.setdefault(kn.group(1), []).append({"capture": m.group(1), "tag": parts[0] + "." + parts[1], "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                                                     "duration": f"{dur.group(1)} {dur.group(2)}" if dur else None})
 # bench.py reads {kernel: {"dram_bytes_per_launch": mean over the captured launches}}
 js = {k: {"dram_bytes_per_launch": sum(c["dram_bytes_per_launch"] for c in v) / len(v), "captures": v} for k, v in traffic.items()}
