@@ -161,6 +161,12 @@ int tem_augment(const void* in, int in_dtype, const float meanstd[2], float* out
    scratch: 32 zeroed bytes of device memory, left zeroed. */
 int tem_mean_var(const float* in, int64_t n, void* scratch, float* out, void* stream);
 
+/* ---- chunked output ---- */
+/* model_cloudrun/transferem.py:171-184: re-tiles the uint8 result volume vol[z,y,x] into chunk^3 blocks (clipped at the volume
+   edge), each block contiguous in C order, blocks concatenated z-outer / y / x-inner: block (bz,by,bx) starts at byte
+   z0*Y*X + cz*(y0*X + cy*x0) of out (z0 = bz*chunk, cz = its clipped depth, ...).  out has Z*Y*X bytes. */
+int tem_chunk_volume(const uint8_t* vol, const int64_t dims_zyx[3], int32_t chunk, uint8_t* out, void* stream);
+
 /* ---- per-op entry points (tests, layer-level parity) ---- */
 typedef struct {
   /* geometry */

@@ -228,6 +228,30 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
   adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale); ++g_tem_launches;
   return cudaGetLastError();
 }
+// ---- chunked output (model_cloudrun/transferem.py:171-184): the zyx result volume re-tiled into c^3 blocks, every block
+// contiguous (C order, clipped at the volume edge), blocks concatenated in the reference's z-outer / y / x-inner order ----
+__global__ void chunk_volume_kernel(const uint8_t* vol, long long Z, long long Y, long long X, int c, uint8_t* out) {
+  const long long nbx = (X + c - 1) / c, nby = (Y + c - 1) / c;
+  long long blk = blockIdx.x;
+  const long long bx = blk % nbx; blk /= nbx; const long long by = blk % nby; const long long bz = blk / nby;
+  const long long z0 = bz * c, y0 = by * c, x0 = bx * c;
+  const long long cz = min((long long)c, Z - z0), cy = min((long long)c, Y - y0), cx = min((long long)c, X - x0);
+  // bytes before this block: full z-layers of blocks, full y-rows of blocks in this layer, blocks before it in its row
+  const long long before = z0 * Y * X + cz * (y0 * X + cy * x0);
+  uint8_t* dst = out + before;
+  const long long n = cz * cy * cx;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long x = i % cx, r = i / cx, y = r % cy, z = r / cy;
+    dst[i] = vol[((z0 + z) * Y + y0 + y) * X + x0 + x];
+  }
+}
+cudaError_t launch_chunk_volume(const uint8_t* vol, long long Z, long long Y, long long X, int c, uint8_t* out, cudaStream_t st) {
+  const long long nb = ((Z + c - 1) / c) * ((Y + c - 1) / c) * ((X + c - 1) / c);
+  if (nb == 0) return cudaSuccess;
+  chunk_volume_kernel<<<(unsigned)nb, 256, 0, st>>>(vol, Z, Y, X, c, out); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
 // ---- input conditioning on device (datasets.py:123-155 augment, :173-190 get_meanstd) ----
 // augment: tf.transpose(perm) -> tf.reverse on the flipped axes -> *= var_adj -> += mean_adj, per sample; with a uint8
 // source the scale_tensor + standardize_population steps that precede it in the reference pipeline are fused in front.

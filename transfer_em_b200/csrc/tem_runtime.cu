@@ -1107,6 +1107,11 @@ extern "C" int tem_unstandardize_to_u8(const float* in, uint8_t* out, int64_t n,
   TEM_CUDA(launch_unstandardize_u8(in, out, n, ms[0], ms[1], (cudaStream_t)stream));
   return TEM_OK;
 }
+extern "C" int tem_chunk_volume(const uint8_t* vol, const int64_t dims[3], int32_t chunk, uint8_t* out, void* stream) {
+  if (!vol || !dims || !out || chunk < 1 || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) ARG_FAIL("tem_chunk_volume: bad arguments");
+  TEM_CUDA(launch_chunk_volume(vol, dims[0], dims[1], dims[2], chunk, out, (cudaStream_t)stream));
+  return TEM_OK;
+}
 extern "C" int tem_augment(const void* in, int in_dtype, const float meanstd[2], float* out, int32_t B, const int32_t out_dims[3],
                            const int32_t* perm, const int32_t* flip, const float* var_adj, const float* mean_adj, void* stream) {
   if (!in || !out || !out_dims || !perm || !flip || !var_adj || !mean_adj || B < 0) ARG_FAIL("tem_augment: bad arguments");

@@ -84,3 +84,47 @@ def predict_cube_from_saved_model(location, start, size, cloudrun, model_dir, fe
     eng = load_saved_model(model_dir)
     return predict_ng_cube(location, start, size, eng, meta["meanstd_x"], meta["meanstd_y"], cloudrun,
                            outdimsize=meta["outdimsize"], buffer=meta["buffer"], fetch_input=fetch_input)
+
+
+def chunk_volume(volume_zyx, chunk=64, device=None):
+    """The blocks of model_cloudrun/transferem.py:171-184, re-tiled on device: returns a list of
+    ((x0, y0, z0), bytes) in the reference's iteration order (z outer, y, x inner); every block is the C-order bytes of
+    volume[z0:z0+chunk, y0:y0+chunk, x0:x0+chunk] (clipped at the volume edge), i.e. `block.tobytes()` of the reference."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .engine import _as_device, _stream
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    t, _ = _as_device(volume_zyx, dev, (torch.uint8,))
+    t = t.contiguous()
+    Z, Y, X = [int(v) for v in t.shape]
+    out = torch.empty(Z * Y * X, dtype=torch.uint8, device=t.device)
+    dims = (C.c_int64 * 3)(Z, Y, X)
+    _lib.check(_lib.load().tem_chunk_volume(C.c_void_p(t.data_ptr()), dims, chunk, C.c_void_p(out.data_ptr()), _stream()))
+    host = out.cpu().numpy()
+    blocks = []
+    for z0 in range(0, Z, chunk):
+        cz = min(chunk, Z - z0)
+        for y0 in range(0, Y, chunk):
+            cy = min(chunk, Y - y0)
+            for x0 in range(0, X, chunk):
+                cx = min(chunk, X - x0)
+                off = z0 * Y * X + cz * (y0 * X + cy * x0)
+                blocks.append(((x0, y0, z0), host[off:off + cz * cy * cx].tobytes()))
+    return blocks
+
+
+def write_ng_chunks(volume_zyx, dest_dir, offset_xyz=(0, 0, 0), chunk=64, compress=True, device=None):
+    """model_cloudrun/transferem.py:158-184 with a local directory in place of the GCS bucket: one file per 64^3 block named
+    "{x0}-{x0+64}_{y0}-{y0+64}_{z0}-{z0+64}" (offsets added, the +64 is NOT clipped, as in the reference), gzip-compressed
+    raw bytes.  Returns the list of file names."""
+    import gzip
+    os.makedirs(dest_dir, exist_ok=True)
+    names = []
+    ox, oy, oz = offset_xyz
+    for (x0, y0, z0), raw in chunk_volume(volume_zyx, chunk, device):
+        name = f"{x0 + ox}-{x0 + chunk + ox}_{y0 + oy}-{y0 + chunk + oy}_{z0 + oz}-{z0 + chunk + oz}"
+        with open(os.path.join(dest_dir, name), "wb") as f:
+            f.write(gzip.compress(raw) if compress else raw)
+        names.append(name)
+    return names
