@@ -328,7 +328,9 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   if (t.zcap > kMaxChunk) t.zcap = kMaxChunk;
   const long long cols = (long long)a.B * t.ntx * t.nty;
   int nzc = (a.L[0] + t.zcap - 1) / t.zcap;
-  while (cols * nzc < 2 * 148 && (a.L[0] + nzc) / (nzc + 1) >= 6) ++nzc;
+  static const char* mc_s = getenv("TEM_TC3_MINCHUNK");
+  const int min_chunk = mc_s ? atoi(mc_s) : 3;     // measured: small layers are a serial MMA chain per CTA, finer z chunks spread it over more SMs
+  while (cols * nzc < 2 * 148 && (a.L[0] + nzc) / (nzc + 1) >= min_chunk) ++nzc;
   t.zc = (a.L[0] + nzc - 1) / nzc; t.nzc = (a.L[0] + t.zc - 1) / t.zc;
   t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
   for (int i = 0; i < 3; ++i) { t.out_off[i] = a.out_off[i]; t.ref_off[i] = a.ref_off[i]; }
