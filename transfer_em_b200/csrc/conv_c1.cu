@@ -134,14 +134,19 @@ __global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const 
   }
 }
 
-// CI -> 1 channel, fp32 output (linear), bf16 input staged as 8-channel planes of uint4
+// CI -> 1 channel, fp32 output (linear), bf16 input staged as 8-channel planes of uint4.  flip = 1: the data gradient of a
+// 1 -> CI first layer (g0 / d0 into the fakes, cgan.py:161,170): taps reversed, zero padding 2, a window of the padded input
+// (conv_off) and accumulation into the fp32 gradient.
 template <int CI>
-__global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz) {
+__global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz, const int flip) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* tile = reinterpret_cast<uint4*>(smem_raw);                 // [CI/8][HZ][HY][HX]
   __shared__ __align__(16) float wsm[27 * CI];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 27 * CI; i += 256) wsm[i] = bf2f(__float2bfloat16_rn(a.w[(i / CI) * a.ws_tap + (long long)(i % CI) * a.ws_in]));
+  for (int i = tid; i < 27 * CI; i += 256) {
+    const int tap = flip ? 26 - i / CI : i / CI;
+    wsm[i] = bf2f(__float2bfloat16_rn(a.w[tap * a.ws_tap + (long long)(i % CI) * a.ws_in]));
+  }
   int t = blockIdx.x;
   const int tx = t % ntx; t /= ntx;
   const int ty = t % nty; t /= nty;
@@ -149,12 +154,13 @@ __global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const
   const int b = t;
   const int z0 = tz * TZ, y0 = ty * TY, x0 = tx * TXT;
   const SrcView& S = a.s0;
+  const int pad = flip ? 2 : 0;
   constexpr int HV = HZc * HYc * HXc, PL = CI / 8;
   const bf16* Sb = reinterpret_cast<const bf16*>(S.p) + (long long)b * S.bstride;
   for (int i = tid; i < HV * PL; i += 256) {
     const int pl = i % PL; const int v = i / PL;
     const int hx = v % HXc; const int r = v / HXc; const int hy = r % HYc; const int hz = r / HYc;
-    const int z = z0 + hz + S.shift[0], y = y0 + hy + S.shift[1], x = x0 + hx + S.shift[2];
+    const int z = z0 + hz + a.conv_off[0] - pad + S.shift[0], y = y0 + hy + a.conv_off[1] - pad + S.shift[1], x = x0 + hx + a.conv_off[2] - pad + S.shift[2];
     uint4 q = make_uint4(0, 0, 0, 0);
     if (z >= 0 && z < S.Z && y >= 0 && y < S.Y && x >= 0 && x < S.X)
       q = __ldg(reinterpret_cast<const uint4*>(Sb + (((long long)z * S.Y + y) * S.X + x) * S.C + S.coff + pl * 8));
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const
     if (oz_ >= a.L[0]) break;
     float v = acc[j];
     if (a.slope != 1.f) v = v > 0.f ? v : v * a.slope;
-    out[((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff] = v;
+    float* op = out + ((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff;
+    *op = a.accumulate ? *op + v : v;
   }
 }
 
@@ -340,14 +347,15 @@ static cudaError_t launch_c1in_v2(const ConvArgs& a, cudaStream_t st) {
 }  // namespace
 
 bool conv_c1_supported(const ConvArgs& a) {
-  if (a.C1 != 0 || a.bias || a.accumulate) return false;
-  for (int i = 0; i < 3; ++i) if (a.k[i] != 3 || a.stride[i] != 1 || a.conv_off[i]) return false;
-  if (a.C0 == 1 && (a.Cout == 8 || a.Cout == 16) && a.out_dtype == DT_BF16 && a.out_C % 8 == 0 && a.out_coff % 8 == 0 &&
+  if (a.C1 != 0 || a.bias) return false;
+  for (int i = 0; i < 3; ++i) if (a.k[i] != 3 || a.stride[i] != 1) return false;
+  const bool plain = !a.accumulate && !a.conv_off[0] && !a.conv_off[1] && !a.conv_off[2];
+  if (plain && a.C0 == 1 && (a.Cout == 8 || a.Cout == 16) && a.out_dtype == DT_BF16 && a.out_C % 8 == 0 && a.out_coff % 8 == 0 &&
       (!a.ref || (a.ref_C % 8 == 0 && a.ref_coff % 8 == 0)))
     return true;                                                     // 1 -> C (form 0 forward, form 1 = flipped + pad 2)
-  if (a.form == 0 && a.Cout == 1 && a.out_dtype == DT_F32 && a.s0.dtype == DT_BF16 && (a.C0 == 8 || a.C0 == 16 || a.C0 == 32) &&
+  if ((a.form == 0 ? plain : true) && a.Cout == 1 && a.out_dtype == DT_F32 && a.s0.dtype == DT_BF16 && (a.C0 == 8 || a.C0 == 16 || a.C0 == 32) &&
       a.s0.C % 8 == 0 && a.s0.coff % 8 == 0 && !a.s0.origins && !a.ref && !a.drop_key)
-    return true;                                                     // C -> 1 forward
+    return true;                                                     // C -> 1 forward; form 1 = data gradient of a 1 -> C layer
   return false;
 }
 
@@ -367,9 +375,10 @@ cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st) {
       e = cudaFuncSetAttribute(conv_c1out_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); if (e) return e;
       attr = true;
     }
-    if (a.C0 == 8) conv_c1out_kernel<8><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
-    else if (a.C0 == 16) conv_c1out_kernel<16><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
-    else conv_c1out_kernel<32><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz);
+    const int flip = a.form == 1;
+    if (a.C0 == 8) conv_c1out_kernel<8><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz, flip);
+    else if (a.C0 == 16) conv_c1out_kernel<16><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz, flip);
+    else conv_c1out_kernel<32><<<(unsigned)grid, 256, smem, st>>>(a, ntx, nty, ntz, flip);
   }
   ++g_tem_launches;
   return cudaGetLastError();
