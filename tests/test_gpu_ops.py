@@ -265,6 +265,11 @@ WG_CASES = [
     (4, 2, 8, 8, True, (9, 11, 19)),
     (4, 2, 32, 32, True, (4, 5, 6)),
     (4, 2, 8, 32, True, (7, 6, 17)),
+    # wide tcgen05 weight gradient (wgrad_tcw.cu): M = 64 / 128 / two 128-channel blocks, ragged rows / column blocks / z chunks
+    (3, 1, 64, 32, False, (7, 9, 37)),
+    (3, 1, 128, 64, False, (6, 11, 20)),
+    (3, 1, 256, 32, False, (5, 7, 10)),
+    (3, 1, 64, 96, False, (13, 6, 35)),
 ]
 
 

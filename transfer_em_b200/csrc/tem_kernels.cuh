@@ -148,6 +148,10 @@ cudaError_t launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);
 bool wgrad_tc_s2_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tc_s2(const WgradArgs& a, cudaStream_t st);
 
+// wgrad_tcw.cu: tcgen05 weight gradient of the wide 3x3x3 stride-1 layers (channel planes fill M, one dz per CTA)
+bool wgrad_tcw_supported(const WgradArgs& a);
+cudaError_t launch_wgrad_tcw(const WgradArgs& a, cudaStream_t st);
+
 // wgrad_tma.cu: TMA-staged, z-marching version of the tensor-core weight gradient
 bool wgrad_tma_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tma(const WgradArgs& a, cudaStream_t st);

@@ -1,0 +1,222 @@
+// tcgen05 weight gradient of the WIDE 3x3x3 stride-1 layers (Ca multiple of 64, Cb multiple of 32: the wf <= 2 models of
+// BASELINE config 4):   dw[(dz,dy,dx)][ca][cb] = sum_{b,v} x[b, v + (dz,dy,dx)][ca] * g[b, v][cb].
+//
+// With 64+ input channels the channel planes alone fill the M dimension, so the row trick of wgrad_tc.cu is not needed:
+//   D_tap[M = 64|128 input channels][N = 32 output channels] += X_tap^T[M][K = 16 voxels of a row] * G[K][N]
+// with MN-major operands read straight from the [voxel][8ch] planes TMA writes (M / N groups = channel planes, uniform
+// plane stride; K groups = 8 consecutive voxels).  A tap (dy,dx) is a shifted start address of the x operand; dz is the
+// z offset of the x tile (blockIdx.y), so one CTA owns 9 accumulators (288 TMEM columns) for (dz, 32 output channels,
+// one block of input channels) and is persistent over (sample, 4 g-rows, 32-voxel column block, z chunk) work units.
+// No MMA work is wasted (every (row, run, tap) MMA is useful), per MMA ~ (4 KB + 1 KB)/128 + 16 cycles.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "tem_kernels.cuh"
+#include "ptx_sm100.cuh"
+
+extern unsigned long long g_tem_launches;
+
+namespace {
+
+constexpr int XB = 2;                        // 16-voxel runs per column block
+constexpr int RB = 4;                        // g rows per work unit
+constexpr int RA = RB + 2;
+constexpr int WB = 16 * XB, WA = 16 * XB + 8;
+constexpr int NBW = 32;                      // output channels per CTA (MMA N)
+constexpr int XRW = 2, GRW = 3;              // ring depths
+constexpr int kThreads = 192;
+
+struct WwArgs {
+  int B, L[3];
+  int M;                       // 64 or 128 input channels per CTA
+  int n_ca, n_cb;              // channel blocks
+  int shift[3];
+  int nrg, ncb, nzc, zc, units;
+  int xa_bytes, gb_bytes;
+  float* dw; long long ws_tap, ws_a, ws_b;
+};
+
+__device__ __forceinline__ uint64_t desc_mn(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const WwArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t xfull[XRW], xempty[XRW], gfull[GRW], gempty[GRW], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* xring = smem;
+  uint8_t* gring = smem + (size_t)XRW * a.xa_bytes;
+  int y = blockIdx.y;
+  const int cab = y % a.n_ca; y /= a.n_ca;
+  const int cbb = y % a.n_cb; y /= a.n_cb;
+  const int dz = y;
+  const int pa = a.M >> 3;                       // planes of the x tile
+  const int xplane = RA * WA * 16, gplane = RB * WB * 16;
+
+  auto decode = [&](int u, int& b, int& y0, int& x0, int& z0, int& nz) {
+    const int zc_i = u % a.nzc; u /= a.nzc;
+    const int cb = u % a.ncb; u /= a.ncb;
+    const int rg = u % a.nrg; u /= a.nrg;
+    b = u; y0 = rg * RB; x0 = cb * WB; z0 = zc_i * a.zc;
+    nz = min(a.zc, a.L[0] - z0);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XRW; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < GRW; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // convergent producer: the whole warp walks the work list, one elected lane issues the TMA loads of a step
+    int xslot = 0; uint32_t xph = 0; int gslot = 0; uint32_t gph = 0;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+      int b, y0, x0, z0, nz; decode(u, b, y0, x0, z0, nz);
+      for (int s = 0; s < nz; ++s) {
+        mbar_wait(&gempty[gslot], gph ^ 1u);
+        mbar_wait(&xempty[xslot], xph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&gfull[gslot], (uint32_t)a.gb_bytes);
+          uint8_t* gd = gring + (size_t)gslot * a.gb_bytes;
+#pragma unroll
+          for (int p = 0; p < NBW / 8; ++p) tma_load_5d(gd + p * gplane, &mapg, &gfull[gslot], (cbb * (NBW / 8) + p) * 8, x0, y0, z0 + s, b);
+          mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
+          uint8_t* xd = xring + (size_t)xslot * a.xa_bytes;
+          for (int p = 0; p < pa; ++p)
+            tma_load_5d(xd + p * xplane, &mapx, &xfull[xslot], (cab * pa + p) * 8, x0 + a.shift[2], y0 + a.shift[1], z0 + s + dz + a.shift[0], b);
+        }
+        __syncwarp();
+        if (++gslot == GRW) { gslot = 0; gph ^= 1u; }
+        if (++xslot == XRW) { xslot = 0; xph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NBW >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+    const uint32_t lo_fixed = (128u >> 4) << 16;                                   // LBO = 128 B (next 8 voxels)
+    const uint32_t a_hi = ((uint32_t)xplane >> 4) | (1u << 14), b_hi = ((uint32_t)gplane >> 4) | (1u << 14);   // SBO = plane stride
+    const uint32_t xbase16 = smem_u32(xring) >> 4, gbase16 = smem_u32(gring) >> 4;
+    const uint32_t xa16 = (uint32_t)a.xa_bytes >> 4, gb16 = (uint32_t)a.gb_bytes >> 4;
+    int xslot = 0; uint32_t xph = 0; int gslot = 0; uint32_t gph = 0;
+    uint32_t acc = 0u;
+    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+      int b, y0, x0, z0, nz; decode(u, b, y0, x0, z0, nz);
+      for (int s = 0; s < nz; ++s) {
+        mbar_wait(&gfull[gslot], gph);
+        mbar_wait(&xfull[xslot], xph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t xs = (xbase16 + (uint32_t)xslot * xa16) | lo_fixed;
+        const uint32_t gs = (gbase16 + (uint32_t)gslot * gb16) | lo_fixed;
+        if (elect_one()) {
+#pragma unroll 1
+          for (int j = 0; j < RB; ++j) {
+#pragma unroll
+            for (int r = 0; r < XB; ++r) {
+              const uint64_t bd = desc_mn(gs + (uint32_t)(j * WB + 16 * r), b_hi);
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint64_t ad = desc_mn(xs + (uint32_t)((j + t / 3) * WA + 16 * r + t % 3), a_hi);
+                umma_bf16(tmem_base + (uint32_t)(t * NBW), ad, bd, idesc, acc);
+              }
+              acc = 1u;
+            }
+          }
+          umma_commit(&xempty[xslot]);
+          umma_commit(&gempty[gslot]);
+        }
+        __syncwarp();
+        acc = 1u;
+        if (++gslot == GRW) { gslot = 0; gph ^= 1u; }
+        if (++xslot == XRW) { xslot = 0; xph ^= 1u; }
+      }
+    }
+    if (elect_one()) umma_commit(&done_bar);
+    __syncwarp();
+  } else {
+    // epilogue: row = input channel of this block, 9 accumulators x 32 output channels -> global atomics
+    mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int m = (a.M == 128) ? q * 32 + lane : q * 16 + (lane & 15);
+    const bool rowok = (a.M == 128) || lane < 16;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ca = cab * a.M + m;
+    const bool any = blockIdx.x < (unsigned)a.units;          // CTAs without work hold an uninitialised accumulator
+    for (int t = 0; t < 9; ++t) {
+      float* dst = a.dw + (long long)(dz * 9 + t) * a.ws_tap + (long long)ca * a.ws_a + (long long)(cbb * NBW) * a.ws_b;
+#pragma unroll
+      for (int c = 0; c < NBW; c += 8) {
+        uint32_t r[8];
+        tmem_ld8(lane_base + (uint32_t)(t * NBW + c), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rowok && any) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float v = __uint_as_float(r[e]);
+            if (v != 0.f) atomicAdd(dst + (long long)(c + e) * a.ws_b, v);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+bool wgrad_tcw_supported(const WgradArgs& w) {
+  if (w.S.dtype != DT_BF16 || w.p_dtype != DT_BF16 || w.S.origins || w.use_lut) return false;
+  for (int i = 0; i < 3; ++i) if (w.k[i] != 3 || w.stride[i] != 1 || w.pad[i] != 0 || w.p_off[i] != 0) return false;
+  if (w.Ca < 64 || w.Ca % 64 || (w.Ca > 64 && w.Ca % 128) || w.Cb < 32 || w.Cb % 32) return false;
+  if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
+  if (w.PZ != w.L[0] || w.PY != w.L[1] || w.PX != w.L[2]) return false;
+  if (w.p_bstride != (long long)w.L[0] * w.L[1] * w.L[2] * w.Cb) return false;
+  if (w.S.bstride != (long long)w.S.Z * w.S.Y * w.S.X * w.S.C) return false;
+  return tem_get_encode() != nullptr;
+}
+
+cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
+  if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
+  WwArgs t; memset(&t, 0, sizeof(t));
+  t.B = w.B; for (int i = 0; i < 3; ++i) { t.L[i] = w.L[i]; t.shift[i] = w.S.shift[i]; }
+  t.M = w.Ca >= 128 ? 128 : 64;
+  t.n_ca = w.Ca / t.M; t.n_cb = w.Cb / NBW;
+  t.xa_bytes = (t.M / 8) * RA * WA * 16; t.gb_bytes = (NBW / 8) * RB * WB * 16;
+  t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
+  t.nrg = (w.L[1] + RB - 1) / RB; t.ncb = (w.L[2] + WB - 1) / WB;
+  const int gy = 3 * t.n_ca * t.n_cb;
+  int gx = 148 / gy; if (gx < 1) gx = 1;
+  // z chunks: enough units for the persistent CTAs of one (dz, channel block) group
+  const long long cols = (long long)w.B * t.nrg * t.ncb;
+  int nzc = 1;
+  while (cols * nzc < 4LL * gx && (w.L[0] + nzc) / (nzc + 1) >= 4) ++nzc;
+  t.zc = (w.L[0] + nzc - 1) / nzc; t.nzc = (w.L[0] + t.zc - 1) / t.zc;
+  t.units = (int)(cols * t.nzc);
+  if (gx > t.units) gx = t.units;
+  CUtensorMap mx, mg;
+  if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, WA, RA)) return cudaErrorInvalidValue;
+  if (!tem_make_map_5d(&mg, w.P, w.B, w.PZ, w.PY, w.PX, w.p_C, WB, RB)) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)XRW * t.xa_bytes + (size_t)GRW * t.gb_bytes + 1024;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  static bool attr = false;
+  if (!attr) { cudaError_t e = cudaFuncSetAttribute(wgrad_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr = true; }
+  wgrad_tcw_kernel<<<dim3((unsigned)gx, (unsigned)gy), kThreads, smem, st>>>(mx, mg, t); ++g_tem_launches;
+  return cudaGetLastError();
+}
