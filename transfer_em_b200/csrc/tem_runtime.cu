@@ -655,7 +655,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   if ((rc = alloc_disc_pass(h, h->dp[4], B, h->dm))) return fail(rc);
   if ((rc = dev_alloc(h, (void**)&h->tile_origins, (size_t)B * 3 * sizeof(int)))) return fail(rc);
   if ((rc = dev_alloc(h, (void**)&h->tile_index, (size_t)B * 3 * sizeof(int)))) return fail(rc);
-  h->h_tile_origins = h->h_tile_index = nullptr;
+  h->h_tile_origins = h->h_tile_index = nullptr; h->tile_cap = B;
   if (cudaDeviceSynchronize() != cudaSuccess) { tem_set_error("device sync failed after init"); return fail(TEM_ERR_CUDA); }
   *out = h;
   return TEM_OK;
@@ -1051,41 +1051,55 @@ extern "C" int tem_predict_volume(tem_handle* h, int net, const uint8_t* vol, co
   if (size[0] <= 0 || size[1] <= 0 || size[2] <= 0) ARG_FAIL("empty request");
   const long long nx = (size[0] + od - 1) / od, ny = (size[1] + od - 1) / od, nz = (size[2] + od - 1) / od;
   if (tz_begin < 0) tz_begin = 0; if (tz_end < 0 || tz_end > nz) tz_end = (int)nz;
-  if (!h->h_tile_origins) {
-    TEM_CUDA(cudaMallocHost((void**)&h->h_tile_origins, (size_t)h->maxB * 3 * sizeof(int) * 2));
-    h->h_tile_index = h->h_tile_origins + (size_t)h->maxB * 3;
-  }
   const int T = h->maxB;
   GenPass& P = h->gp[6];
   // tile order of the reference: x outer, y, z inner (utils.py:78-84); restricted to the z slab
   long long done = 0;
   const long long total = nx * ny * (tz_end - tz_begin);
+  if (vd[0] > 2147483647LL || vd[1] > 2147483647LL || vd[2] > 2147483647LL) ARG_FAIL("volume too large");
+  // The origin / index tables of the WHOLE request are built once and uploaded with one copy pair: batches then run back
+  // to back without a host synchronisation between them (the reference syncs per tile, utils.py:111-112).
+  TEM_CUDA(cudaStreamSynchronize(st));                  // a previous request may still read the pinned staging
+  if (!h->h_tile_origins || total > h->tile_cap) {
+    const long long cap = std::max<long long>(total, h->tile_cap);
+    if (h->h_tile_origins) TEM_CUDA(cudaFreeHost(h->h_tile_origins));
+    h->h_tile_origins = nullptr;
+    TEM_CUDA(cudaMallocHost((void**)&h->h_tile_origins, (size_t)cap * 3 * sizeof(int) * 2));
+    h->h_tile_index = h->h_tile_origins + (size_t)cap * 3;
+    if (cap > h->tile_cap) {                            // the old device tables stay in h->allocs until tem_destroy
+      TEM_CHECK(dev_alloc(h, (void**)&h->tile_origins, (size_t)cap * 3 * sizeof(int)));
+      TEM_CHECK(dev_alloc(h, (void**)&h->tile_index, (size_t)cap * 3 * sizeof(int)));
+    }
+    h->tile_cap = cap;
+  }
+  for (long long t = 0; t < total; ++t) {
+    long long id = t;
+    const long long zi = tz_begin + id % (tz_end - tz_begin); id /= (tz_end - tz_begin);
+    const long long yi = id % ny; const long long xi = id / ny;
+    const long long x0 = start[0] + xi * od, y0 = start[1] + yi * od, z0 = start[2] + zi * od;
+    h->h_tile_origins[t * 3 + 0] = (int)(z0 - buf); h->h_tile_origins[t * 3 + 1] = (int)(y0 - buf); h->h_tile_origins[t * 3 + 2] = (int)(x0 - buf);
+    h->h_tile_index[t * 3 + 0] = (int)(xi * od); h->h_tile_index[t * 3 + 1] = (int)(yi * od); h->h_tile_index[t * 3 + 2] = (int)(zi * od);
+  }
+  if (total > 0) {
+    TEM_CUDA(cudaMemcpyAsync(h->tile_origins, h->h_tile_origins, (size_t)total * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    TEM_CUDA(cudaMemcpyAsync(h->tile_index, h->h_tile_index, (size_t)total * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   InputRef ir; memset(&ir, 0, sizeof(ir));
   ir.p = vol; ir.dtype = DT_U8; set3(ir.dims, (int)vd[0], (int)vd[1], (int)vd[2]);
-  ir.origins = h->tile_origins; ir.use_lut = 1; ir.mean = msx[0]; ir.stdv = msx[1];
-  if (vd[0] > 2147483647LL || vd[1] > 2147483647LL || vd[2] > 2147483647LL) ARG_FAIL("volume too large");
+  ir.use_lut = 1; ir.mean = msx[0]; ir.stdv = msx[1];
   while (done < total) {
     const int nb = (int)std::min<long long>(T, total - done);
-    // the previous batch must have consumed the staging buffers before they are rewritten
-    TEM_CUDA(cudaStreamSynchronize(st));
-    for (int t = 0; t < nb; ++t) {
-      long long id = done + t;
-      const long long zi = tz_begin + id % (tz_end - tz_begin); id /= (tz_end - tz_begin);
-      const long long yi = id % ny; const long long xi = id / ny;
-      const long long x0 = start[0] + xi * od, y0 = start[1] + yi * od, z0 = start[2] + zi * od;
-      h->h_tile_origins[t * 3 + 0] = (int)(z0 - buf); h->h_tile_origins[t * 3 + 1] = (int)(y0 - buf); h->h_tile_origins[t * 3 + 2] = (int)(x0 - buf);
-      h->h_tile_index[t * 3 + 0] = (int)(xi * od); h->h_tile_index[t * 3 + 1] = (int)(yi * od); h->h_tile_index[t * 3 + 2] = (int)(zi * od);
-    }
-    TEM_CUDA(cudaMemcpyAsync(h->tile_origins, h->h_tile_origins, (size_t)nb * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
-    TEM_CUDA(cudaMemcpyAsync(h->tile_index, h->h_tile_index, (size_t)nb * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int* d_orig = h->tile_origins + done * 3;
+    const int* d_idx = h->tile_index + done * 3;
+    ir.origins = d_orig;
     TEM_CHECK(gen_forward(h, net, P, ir, nb, tsz, nullptr, st));
     StitchArgs sa; memset(&sa, 0, sizeof(sa));
-    sa.y = (const float*)P.a[11].p; sa.index = h->tile_index; sa.T = nb; sa.ydim = od + 2 * tpad; sa.tpad = tpad; sa.od = od;
+    sa.y = (const float*)P.a[11].p; sa.index = d_idx; sa.T = nb; sa.ydim = od + 2 * tpad; sa.tpad = tpad; sa.od = od;
     sa.mean = msy[0]; sa.stdv = msy[1]; sa.out = out; sa.OZ = size[2]; sa.OY = size[1]; sa.OX = size[0];
     TEM_CUDA(launch_stitch_u8(sa, st));
     if (in_out) {
       FetchInArgs fa; memset(&fa, 0, sizeof(fa));
-      fa.vol = vol; fa.VZ = vd[0]; fa.VY = vd[1]; fa.VX = vd[2]; fa.origins = h->tile_origins; fa.index = h->tile_index;
+      fa.vol = vol; fa.VZ = vd[0]; fa.VY = vd[1]; fa.VX = vd[2]; fa.origins = d_orig; fa.index = d_idx;
       fa.T = nb; fa.buf = buf; fa.od = od; fa.mean = msx[0]; fa.stdv = msx[1]; fa.out = in_out; fa.OZ = size[2]; fa.OY = size[1]; fa.OX = size[0];
       TEM_CUDA(launch_fetch_input_u8(fa, st));
     }

@@ -86,6 +86,7 @@ struct tem_handle {
   float* dlog[6];              // logit gradients: gen_y, gen_x, dyr, dyf, dxr, dxf
   int* tile_origins; int* tile_index;   // device, maxB*3 each
   int* h_tile_origins; int* h_tile_index;   // pinned host staging
+  long long tile_cap;                       // tiles the device / host tile tables hold (grown per request)
   uint32_t next_keys[12]; bool keys_overridden;
   // communicator
   void* comm; int rank, world;
