@@ -270,6 +270,10 @@ WG_CASES = [
     (3, 1, 128, 64, False, (6, 11, 20)),
     (3, 1, 256, 32, False, (5, 7, 10)),
     (3, 1, 64, 96, False, (13, 6, 35)),
+    (4, 2, 64, 32, False, (10, 14, 38)),      # wide stride-2 (parity-class form of wgrad_tcw)
+    (4, 2, 128, 64, False, (8, 10, 12)),
+    (4, 2, 64, 64, True, (5, 7, 9)),
+    (4, 2, 32, 128, True, (6, 5, 18)),
 ]
 
 

@@ -7,7 +7,7 @@ B = 8
 # name: (k, s, cin, cout, transposed, in_dim)
 L = {'g0': (3,1,1,8,False,74), 'g1': (3,1,8,8,False,72), 'g2': (4,2,8,8,False,70), 'g3': (3,1,8,16,False,34), 'g4': (4,2,16,16,False,32),
      'g5': (3,1,16,32,False,15), 'g6': (4,2,32,16,True,13), 'g7': (3,1,32,32,False,26), 'g8': (3,1,32,16,False,24), 'g9': (4,2,16,8,True,22),
-     'g10': (3,1,16,16,False,44), 'g11': (3,1,16,1,False,42), 'w1': (3,1,64,64,False,72), 'w3': (3,1,64,128,False,34), 'w5': (3,1,128,256,False,15), 'w7': (3,1,256,256,False,26), 'w8': (3,1,256,128,False,24), 'w10': (3,1,128,128,False,44), 'd2': (3,1,8,16,False,18), 'd3': (3,1,16,32,False,16), 'd5': (3,1,32,32,False,6), 'd0': (3,1,1,8,False,40), 'd1': (4,2,8,8,False,38), 'd4': (4,2,32,32,False,14), 'd6': (4,2,32,32,False,4)}
+     'g10': (3,1,16,16,False,44), 'g11': (3,1,16,1,False,42), 'w1': (3,1,64,64,False,72), 'w2': (4,2,64,64,False,70), 'w4': (4,2,128,128,False,32), 'w6': (4,2,256,128,True,13), 'w9': (4,2,128,64,True,22), 'w3': (3,1,64,128,False,34), 'w5': (3,1,128,256,False,15), 'w7': (3,1,256,256,False,26), 'w8': (3,1,256,128,False,24), 'w10': (3,1,128,128,False,44), 'd2': (3,1,8,16,False,18), 'd3': (3,1,16,32,False,16), 'd5': (3,1,32,32,False,6), 'd0': (3,1,1,8,False,40), 'd1': (4,2,8,8,False,38), 'd4': (4,2,32,32,False,14), 'd6': (4,2,32,32,False,4)}
 if len(sys.argv) > 1 and sys.argv[1].startswith('B='): B = int(sys.argv.pop(1)[2:])
 names = sys.argv[1:] or ['g1.fwd', 'g1.dgrad', 'g1.wgrad', 'g0.fwd', 'g0.wgrad', 'g10.wgrad', 'g7.wgrad', 'g2.fwd', 'g2.dgrad', 'g2.wgrad', 'g11.fwd', 'g11.wgrad', 'd6.fwd', 'd4.fwd']
 dev = 'cuda'

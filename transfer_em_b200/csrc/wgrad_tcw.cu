@@ -8,6 +8,8 @@
 // z offset of the x tile (blockIdx.y), so one CTA owns 9 accumulators (288 TMEM columns) for (dz, 32 output channels,
 // one block of input channels) and is persistent over (sample, 4 g-rows, 32-voxel column block, z chunk) work units.
 // No MMA work is wasted (every (row, run, tap) MMA is useful), per MMA ~ (4 KB + 1 KB)/128 + 16 cycles.
+// The 4x4x4 stride-2 layers (strided conv, transposed conv) use the same kernel in parity-class form (see wgrad_tc_s2.cu):
+// blockIdx.y carries (class, m'z), the four (m'y, m'x) taps are the accumulators, x tiles are de-interleaved by TMA.
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
@@ -20,7 +22,7 @@ namespace {
 
 constexpr int XB = 2;                        // 16-voxel runs per column block
 constexpr int RB = 4;                        // g rows per work unit
-constexpr int RA = RB + 2;
+constexpr int RA = RB + 2;                   // x rows of a tile (stride 2 uses RB + 1 of them)
 constexpr int WB = 16 * XB, WA = 16 * XB + 8;
 constexpr int NBW = 32;                      // output channels per CTA (MMA N)
 constexpr int XRW = 2, GRW = 3;              // ring depths
@@ -31,6 +33,7 @@ struct WwArgs {
   int M;                       // 64 or 128 input channels per CTA
   int n_ca, n_cb;              // channel blocks
   int shift[3];
+  int s2, pad;                 // 4x4x4 stride-2 mode: blockIdx.y carries (parity class, m'z) instead of dz; x tiles are de-interleaved by TMA
   int nrg, ncb, nzc, zc, units;
   int xa_bytes, gb_bytes;
   float* dw; long long ws_tap, ws_a, ws_b;
@@ -53,9 +56,15 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
   int y = blockIdx.y;
   const int cab = y % a.n_ca; y /= a.n_ca;
   const int cbb = y % a.n_cb; y /= a.n_cb;
-  const int dz = y;
+  // stride 1: y = dz.  stride 2: y = class * 2 + m'z with class = (rz, ry, rx); k - pad = 2m + r, m = m_lo(r) + m'
+  const int dz = a.s2 ? 0 : y;
+  const int mz = a.s2 ? (y & 1) : 0, cls = a.s2 ? (y >> 1) : 0;
+  const int rz = cls >> 2, ry = (cls >> 1) & 1, rx = cls & 1;
+  auto mlo = [&](int r) { return (((r + a.pad) & 1) - a.pad - r) / 2; };
+  const int ntap = a.s2 ? 4 : 9;
+  const int ra = a.s2 ? RB + 1 : RA;
   const int pa = a.M >> 3;                       // planes of the x tile
-  const int xplane = RA * WA * 16, gplane = RB * WB * 16;
+  const int xplane = ra * WA * 16, gplane = RB * WB * 16;
 
   auto decode = [&](int u, int& b, int& y0, int& x0, int& z0, int& nz) {
     const int zc_i = u % a.nzc; u /= a.nzc;
@@ -95,8 +104,11 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
           for (int p = 0; p < NBW / 8; ++p) tma_load_5d(gd + p * gplane, &mapg, &gfull[gslot], (cbb * (NBW / 8) + p) * 8, x0, y0, z0 + s, b);
           mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
           uint8_t* xd = xring + (size_t)xslot * a.xa_bytes;
+          const int cx = a.s2 ? 2 * (x0 + mlo(rx)) + rx + a.shift[2] : x0 + a.shift[2];
+          const int cy = a.s2 ? 2 * (y0 + mlo(ry)) + ry + a.shift[1] : y0 + a.shift[1];
+          const int cz = a.s2 ? 2 * (z0 + s + mlo(rz) + mz) + rz + a.shift[0] : z0 + s + dz + a.shift[0];
           for (int p = 0; p < pa; ++p)
-            tma_load_5d(xd + p * xplane, &mapx, &xfull[xslot], (cab * pa + p) * 8, x0 + a.shift[2], y0 + a.shift[1], z0 + s + dz + a.shift[0], b);
+            tma_load_5d(xd + p * xplane, &mapx, &xfull[xslot], (cab * pa + p) * 8, cx, cy, cz, b);
         }
         __syncwarp();
         if (++gslot == GRW) { gslot = 0; gph ^= 1u; }
@@ -127,8 +139,11 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
               const uint64_t bd = desc_mn(gs + (uint32_t)(j * WB + 16 * r), b_hi);
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
-                const uint64_t ad = desc_mn(xs + (uint32_t)((j + t / 3) * WA + 16 * r + t % 3), a_hi);
-                umma_bf16(tmem_base + (uint32_t)(t * NBW), ad, bd, idesc, acc);
+                if (t < ntap) {
+                  const int ty = a.s2 ? (t >> 1) : t / 3, tx = a.s2 ? (t & 1) : t % 3;
+                  const uint64_t ad = desc_mn(xs + (uint32_t)((j + ty) * WA + 16 * r + tx), a_hi);
+                  umma_bf16(tmem_base + (uint32_t)(t * NBW), ad, bd, idesc, acc);
+                }
               }
               acc = 1u;
             }
@@ -154,8 +169,13 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ca = cab * a.M + m;
     const bool any = blockIdx.x < (unsigned)a.units;          // CTAs without work hold an uninitialised accumulator
-    for (int t = 0; t < 9; ++t) {
-      float* dst = a.dw + (long long)(dz * 9 + t) * a.ws_tap + (long long)ca * a.ws_a + (long long)(cbb * NBW) * a.ws_b;
+    for (int t = 0; t < ntap; ++t) {
+      int tap = dz * 9 + t;
+      if (a.s2) {
+        const int kz = 2 * (mlo(rz) + mz) + rz + a.pad, ky = 2 * (mlo(ry) + (t >> 1)) + ry + a.pad, kx = 2 * (mlo(rx) + (t & 1)) + rx + a.pad;
+        tap = (kz * 4 + ky) * 4 + kx;
+      }
+      float* dst = a.dw + (long long)tap * a.ws_tap + (long long)ca * a.ws_a + (long long)(cbb * NBW) * a.ws_b;
 #pragma unroll
       for (int c = 0; c < NBW; c += 8) {
         uint32_t r[8];
@@ -183,7 +203,9 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
 
 bool wgrad_tcw_supported(const WgradArgs& w) {
   if (w.S.dtype != DT_BF16 || w.p_dtype != DT_BF16 || w.S.origins || w.use_lut) return false;
-  for (int i = 0; i < 3; ++i) if (w.k[i] != 3 || w.stride[i] != 1 || w.pad[i] != 0 || w.p_off[i] != 0) return false;
+  const bool s1 = w.k[0] == 3 && w.stride[0] == 1 && w.pad[0] == 0, s2 = w.k[0] == 4 && w.stride[0] == 2 && (w.pad[0] == 0 || w.pad[0] == 1);
+  if (!s1 && !s2) return false;
+  for (int i = 0; i < 3; ++i) if (w.k[i] != w.k[0] || w.stride[i] != w.stride[0] || w.pad[i] != w.pad[0] || w.p_off[i] != 0) return false;
   if (w.Ca < 64 || w.Ca % 64 || (w.Ca > 64 && w.Ca % 128) || w.Cb < 32 || w.Cb % 32) return false;
   if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
   if (w.PZ != w.L[0] || w.PY != w.L[1] || w.PX != w.L[2]) return false;
@@ -196,12 +218,14 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
   if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
   WwArgs t; memset(&t, 0, sizeof(t));
   t.B = w.B; for (int i = 0; i < 3; ++i) { t.L[i] = w.L[i]; t.shift[i] = w.S.shift[i]; }
+  t.s2 = w.stride[0] == 2; t.pad = w.pad[0];
   t.M = w.Ca >= 128 ? 128 : 64;
   t.n_ca = w.Ca / t.M; t.n_cb = w.Cb / NBW;
-  t.xa_bytes = (t.M / 8) * RA * WA * 16; t.gb_bytes = (NBW / 8) * RB * WB * 16;
+  const int ra = t.s2 ? RB + 1 : RA;
+  t.xa_bytes = (t.M / 8) * ra * WA * 16; t.gb_bytes = (NBW / 8) * RB * WB * 16;
   t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
   t.nrg = (w.L[1] + RB - 1) / RB; t.ncb = (w.L[2] + WB - 1) / WB;
-  const int gy = 3 * t.n_ca * t.n_cb;
+  const int gy = (t.s2 ? 16 : 3) * t.n_ca * t.n_cb;
   int gx = 148 / gy; if (gx < 1) gx = 1;
   // z chunks: enough units for the persistent CTAs of one (dz, channel block) group
   const long long cols = (long long)w.B * t.nrg * t.ncb;
@@ -211,7 +235,17 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
   t.units = (int)(cols * t.nzc);
   if (gx > t.units) gx = t.units;
   CUtensorMap mx, mg;
-  if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, WA, RA)) return cudaErrorInvalidValue;
+  if (!t.s2) { if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, WA, RA)) return cudaErrorInvalidValue; }
+  else {      // de-interleaved tiles: every second voxel of every second row (element strides), as in conv_tc_s2.cu
+    EncodeTiledFn enc = tem_get_encode();
+    if (!enc) return cudaErrorInvalidValue;
+    cuuint64_t dims[5] = {(cuuint64_t)w.S.C, (cuuint64_t)w.S.X, (cuuint64_t)w.S.Y, (cuuint64_t)w.S.Z, (cuuint64_t)w.B};
+    cuuint64_t strides[4] = {(cuuint64_t)w.S.C * 2, (cuuint64_t)w.S.X * w.S.C * 2, (cuuint64_t)w.S.Y * w.S.X * w.S.C * 2, (cuuint64_t)w.S.Z * w.S.Y * w.S.X * w.S.C * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)(WA * 2), (cuuint32_t)(ra * 2), 1, 1};
+    cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+    if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(w.S.p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
   if (!tem_make_map_5d(&mg, w.P, w.B, w.PZ, w.PY, w.PX, w.p_C, WB, RB)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)XRW * t.xa_bytes + (size_t)GRW * t.gb_bytes + 1024;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
