@@ -139,6 +139,8 @@ int tem_comm_sync_params(tem_handle* h, void* stream);
 /* ---- measurement hooks (bench.py) ---- */
 /* number of kernels this library has launched in this process */
 uint64_t tem_launch_count(void);
+/* name of the kernel function the most recent convolution / weight-gradient call dispatched to (tests assert the path) */
+const char* tem_last_kernel(void);
 /* bracket every convolution launch with CUDA events on its stream, aggregated by "<layer>.<fwd|dgrad|wgrad>" */
 int tem_profile_enable(tem_handle* h, int on);
 /* synchronises, then writes one line per tag: "tag count total_ms algorithmic_bytes_per_launch flops_per_launch" */

@@ -364,6 +364,43 @@ def test_mma_conv_fwd_dgrad(k, s, cin, cout, tr, dims):
     assert rel_l2(dx, dref) < 4e-3
 
 
+WIDE_S2_CASES = [
+    # k, s, cin, cout, transposed, dims: wide 4x4x4 stride-2 layers of the wf <= 4 models (streamed-weight tcgen05 kernels)
+    (4, 2, 64, 64, False, (10, 20, 22)),     # g2 / d1 at wf = 1: fwd = wide DOWN (NP 64, 32-slot weight ring), dgrad = wide UP
+    (4, 2, 128, 128, False, (8, 6, 38)),     # g4 at wf = 1: eight 16-channel chunks, two 64-channel chunks, ragged x tiles
+    (4, 2, 128, 64, True, (5, 9, 18)),       # g9 at wf = 1: fwd = wide UP (Cin 128, two cout groups), dgrad = wide DOWN (NP 128)
+    (4, 2, 64, 32, True, (4, 18, 9)),        # g6 at wf = 4: fwd = wide UP (one cout group), dgrad = wide DOWN (Cin 32)
+    (4, 2, 64, 256, False, (20, 6, 8)),      # NP = 256: two output slices per TMEM strip, several z chunks
+    (4, 2, 64, 40, False, (6, 8, 8)),        # Cout not a multiple of the column groups
+]
+
+
+@pytest.mark.parametrize("k,s,cin,cout,tr,dims", WIDE_S2_CASES)
+def test_wide_stride2_tcgen05_fwd_dgrad(k, s, cin, cout, tr, dims):
+    """conv_upw_tc_kernel / conv_downw_tc_kernel (models/utils.py:80,129-130 at 64-256 channels) vs the naive fp64 oracle."""
+    lib = _lib.load()
+    r = np.random.default_rng(k * 1000 + cin * 10 + cout + int(tr))
+    B = 2
+    x = bf16r(r.standard_normal((B,) + dims + (cin,)))
+    wshape = (k, k, k) + ((cout, cin) if tr else (cin, cout))
+    w = bf16r(r.standard_normal(wshape) * 0.05)
+    d = make_desc(B, dims, cin, cout, k, s, tr, 0.3, 0, tc=1)
+    xg, wg = _cuda(x, torch.bfloat16), _cuda(w, torch.float32)
+    y = conv_forward(xg, wg, d).float().cpu().numpy()
+    assert lib.tem_last_kernel().decode() == ("conv_upw_tc_kernel" if tr else "conv_downw_tc_kernel")
+    ref = naive.lrelu(naive.convT_fwd(x, w) if tr else naive.conv_fwd(x, w, s), 0.3)
+    assert y.shape == ref.shape
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    dy = bf16r(r.standard_normal(ref.shape))
+    act = bf16r(r.standard_normal(x.shape))
+    dx = conv_dgrad(_cuda(dy, torch.bfloat16), wg, d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
+    if tr or cout % 64 == 0:      # the data gradient reads `cout` channels: wide UP needs 64-channel chunks
+        assert lib.tem_last_kernel().decode() == ("conv_downw_tc_kernel" if tr else "conv_upw_tc_kernel")
+    dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
+    assert rel_l2(dx, dref) < 4e-3
+
+
 def test_tcgen05_stride2_dropout_epilogue():
     """Conv3DTranspose forward on the tcgen05 UP kernel with the fused Dropout(0.5) mask (models/utils.py:129-135)."""
     key = 0x1234ABCD

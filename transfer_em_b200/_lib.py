@@ -66,6 +66,7 @@ _SIGS = {
     "tem_comm_world": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tem_comm_sync_params": (C.c_int, [_P, _P]),
     "tem_launch_count": (C.c_uint64, []),
+    "tem_last_kernel": (C.c_char_p, []),
     "tem_profile_enable": (C.c_int, [_P, C.c_int]),
     "tem_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "tem_standardize_u8": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_float), _P]),

@@ -45,7 +45,8 @@ struct S2Args {
   int shift[3];                // tensor coordinate = conv-input coordinate + shift
   int cin8;
   const bf16* wpacked; int wbytes;
-  int ntx, nty, nzc, zc, ring;
+  int ntx, nty, nzc, zc, ring;      // ring: input slots (resident-weight kernels) / weight slots (wide DOWN)
+  int np;                            // wide DOWN: MMA N (columns per output slice)
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
   float slope;
@@ -428,6 +429,410 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// UP, wide layers (Cin multiple of 64, any Cout: wf <= 2).  Same GEMM as conv_up_tc_kernel with CP = 32 (N = 8 classes x
+// 32 output channels = 256 columns, blockIdx.y = group of 32 output channels), but K = 8 taps x Cin no longer fits in
+// shared memory as weights (Cin = 64 already needs 256 KB), so BOTH operands are streamed:
+//   * inputs: per q-slice and 64-channel chunk, the two source slices (qz-1, qz) of that chunk (40 KB stage, 2 stages);
+//   * weights: one K-step (16 channels x 256 columns = 8 KB) per stage through a 12-stage ring, in MMA order.
+// Two producer warps (inputs / weights), one MMA issuer, eight epilogue warps.
+// ------------------------------------------------------------------------------------------------
+constexpr int UW_PL = 8;                                 // planes (64 channels) per input chunk
+constexpr int UW_IN_STAGE = 2 * UW_PL * SUB_STRIDE;      // 40960
+constexpr int UW_NIN = 2;
+constexpr int UW_WSTAGE = 256 * 32;                      // 8192 B: [k-half][32 n-groups][8][8] bf16
+constexpr int UW_NW = 12;
+constexpr int kThreadsUpw = 352;                         // warps: 0 input TMA, 1 MMA, 2-9 epilogue, 10 weight loads
+
+__global__ void __launch_bounds__(kThreadsUpw, 1)
+conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
+  constexpr int CP = 32, NP = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t in_full[UW_NIN], in_empty[UW_NIN], w_full[UW_NW], w_empty[UW_NW], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* inring = smem;
+  uint8_t* wring = smem + UW_NIN * UW_IN_STAGE;
+  const int cg = blockIdx.y, co0 = cg * CP;
+  const int nchunks = a.planes / UW_PL;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < UW_NIN; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < UW_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  int b, x0, y0, z0, nz; decode_work(a, b, x0, y0, z0, nz);
+
+  if (warp == 0) {
+    int slot = 0; uint32_t ph = 0;
+    for (int zo = 0; zo < nz; ++zo)
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&in_empty[slot], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&in_full[slot], (uint32_t)(2 * UW_PL) * SUB_BYTES);
+          uint8_t* dst = inring + (size_t)slot * UW_IN_STAGE;
+          for (int sl = 0; sl < 2; ++sl)
+            for (int p = 0; p < UW_PL; ++p)
+              tma_load_5d(dst + (sl * UW_PL + p) * SUB_STRIDE, &map0, &in_full[slot], (c * UW_PL + p) * 8, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 + zo - 1 + sl + a.shift[0], b);
+        }
+        __syncwarp();
+        if (++slot == UW_NIN) { slot = 0; ph ^= 1u; }
+      }
+  } else if (warp == 10) {
+    int slot = 0; uint32_t ph = 0;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nchunks * 32 * UW_WSTAGE;
+    for (int zo = 0; zo < nz; ++zo)
+      for (int st = 0; st < nchunks * 32; ++st) {       // stage order = MMA order: chunk, tap (mz,my,mx), 16-channel step
+        mbar_wait(&w_empty[slot], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)UW_WSTAGE);
+          bulk_load(wring + (size_t)slot * UW_WSTAGE, wsrc + (size_t)st * UW_WSTAGE, (uint32_t)UW_WSTAGE, &w_full[slot]);
+        }
+        __syncwarp();
+        if (++slot == UW_NW) { slot = 0; ph ^= 1u; }
+      }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = ((uint32_t)SUB_STRIDE >> 4) << 16;            // K halves = two consecutive planes
+    const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;             // K halves of a weight stage
+    const uint32_t in16 = smem_u32(inring) >> 4, w16 = smem_u32(wring) >> 4;
+    int islot = 0; uint32_t iph = 0; int wslot = 0; uint32_t wph = 0;
+    for (int zo = 0; zo < nz; ++zo) {
+      mbar_wait(&tempty_bar[zo & 1], (((uint32_t)(zo >> 1)) & 1u) ^ 1u);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(zo & 1) * NP;
+      uint32_t acc = 0u;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&in_full[islot], iph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ib16 = in16 + (uint32_t)islot * (UW_IN_STAGE >> 4);
+#pragma unroll 1
+        for (int tap = 0; tap < 8; ++tap) {
+          const int mz = tap >> 2, my = (tap >> 1) & 1, mx = tap & 1;
+#pragma unroll 1
+          for (int kc = 0; kc < UW_PL / 2; ++kc) {
+            mbar_wait(&w_full[wslot], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t alo = (ib16 + (uint32_t)(((mz * UW_PL + 2 * kc) * SUB_STRIDE) >> 4) + (uint32_t)(my * SXV + mx)) | a_lbo;
+              const uint32_t blo = (w16 + (uint32_t)wslot * (UW_WSTAGE >> 4)) | b_lbo;
+              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+              umma_commit(&w_empty[wslot]);
+            }
+            __syncwarp();
+            acc = 1u;
+            if (++wslot == UW_NW) { wslot = 0; wph ^= 1u; }
+          }
+        }
+        if (elect_one()) {
+          umma_commit(&in_empty[islot]);
+          if (c == nchunks - 1) umma_commit(&tfull_bar[zo & 1]);
+        }
+        __syncwarp();
+        if (++islot == UW_NIN) { islot = 0; iph ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int rz = (warp - 2) >> 2;                // output z parity handled by this warp
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int qy = y0 + yl, qx = x0 + xl;
+    constexpr int NCH = CP / 8;
+    for (int zo = 0; zo < nz; ++zo) {
+      const int qz = z0 + zo;
+      const int oz = 2 * qz + rz - a.pad;
+      const bool zok = oz >= 0 && oz < a.L[0];
+      mbar_wait(&tfull_bar[zo & 1], ((uint32_t)(zo >> 1)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo & 1) * NP + (uint32_t)(rz * 4 * CP);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        __syncwarp();
+        const int oy = 2 * qy + (c4 >> 1) - a.pad, ox = 2 * qx + (c4 & 1) - a.pad;
+        const bool ok = zok && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2];
+        uint4 refq[NCH], accq[NCH];
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (co0 + c * 8 < a.Cout) {
+              if (a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0 + c * 8));
+              if (a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + co0 + c * 8);
+            }
+          }
+        }
+        uint32_t r[CP];
+#pragma unroll
+        for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + (uint32_t)(c4 * CP + c), r + c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c4 == 3) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tempty_bar[zo & 1]);
+        }
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (co0 + c * 8 < a.Cout) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
+              Epi::run(a, v, co0 + c * 8, b, oz, oy, ox, refq[c], accq[c]);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// weight stages of the wide UP kernel: [cout group][chunk][tap = (mz,my,mx)][kc][k-half][n-group (32)][8][8], n = class*32 + co
+struct PackUpwArgs { const float* w; long long ws_tap, ws_in, ws_out; int nchunks, cout; bf16* dst; long long total; };
+__global__ void pack_weights_upw_kernel(const PackUpwArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  long long t = i;
+  const int e = (int)(t & 7); t >>= 3;
+  const int r = (int)(t & 7); t >>= 3;
+  const int g = (int)(t & 31); t >>= 5;
+  const int j = (int)(t & 1); t >>= 1;
+  const int kc = (int)(t & 3); t >>= 2;
+  const int tap = (int)(t & 7); t >>= 3;
+  const int c = (int)(t % a.nchunks); t /= a.nchunks;
+  const int cg = (int)t;
+  const int n = g * 8 + r, cls = n >> 5, co = cg * 32 + (n & 31);
+  const int rz = cls >> 2, ry = (cls >> 1) & 1, rx = cls & 1;
+  const int mz = tap >> 2, my = (tap >> 1) & 1, mx = tap & 1;
+  const int kz = rz + 2 * (1 - mz), ky = ry + 2 * (1 - my), kx = rx + 2 * (1 - mx);
+  const int ci = c * 64 + (2 * kc + j) * 8 + e;
+  float v = 0.f;
+  if (co < a.cout) v = a.w[(long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)ci * a.ws_in + (long long)co * a.ws_out];
+  a.dst[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DOWN, wide layers (Cin multiple of 16, Cout up to 256 per CTA: wf <= 4).  N = NP = Cout rounded to 64 columns; the
+// K = 64 taps x Cin reduction is split into 16-channel chunks (one K-step = two planes) and the CTA owns a TMEM strip of
+// ZS = 512 / NP output slices that stays resident over all chunks (the conv_tcw.cu recipe), so that every input slice
+// pair (2j, 2j+1) of a chunk is staged ONCE and feeds both output slices that read it (zo = j with kz = 0,1 and
+// zo = j - 1 with kz = 2,3).  Weights are streamed in MMA order, one K-step (16 x NP) per ring slot.
+//   input stage : [slice 2][parity (ry,rx) 4][plane 2] de-interleaved sub-tiles = 40 KB, 3 stages
+//   weight stage: NP x 32 B, ring of 80 KB
+// Warps: 0 input TMA, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quadrant, half of the columns each), 10 weights.
+// ------------------------------------------------------------------------------------------------
+constexpr int DW_STAGE = 16 * SUB_STRIDE;                // 40960
+constexpr int DW_NIN = 3;
+constexpr int DW_WRING = 80 * 1024;
+constexpr int DW_WMAX = 40;                              // slots at NP = 64
+constexpr int kThreadsDw = 352;
+constexpr int DW_ZMAX = 8;                               // output slices per CTA at NP = 64
+
+__global__ void __launch_bounds__(kThreadsDw, 1)
+conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t in_full[DW_NIN], in_empty[DW_NIN], w_full[DW_WMAX], w_empty[DW_WMAX], tfull_bar[DW_ZMAX];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* inring = smem;
+  uint8_t* wring = smem + DW_NIN * DW_STAGE;
+  const int NP = a.np;
+  const int wstage = NP * 32;
+  const int nw = a.ring;                                 // weight slots
+  const int cg = blockIdx.y, co0 = cg * NP;
+  const int nch = a.planes >> 1;                         // 16-channel chunks
+
+  int b, x0, y0, z0, nz; decode_work(a, b, x0, y0, z0, nz);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DW_NIN; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < nw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < DW_ZMAX; ++i) mbar_init(&tfull_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    int slot = 0; uint32_t ph = 0;
+    for (int c = 0; c < nch; ++c)
+      for (int j = 0; j <= nz; ++j) {
+        mbar_wait(&in_empty[slot], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&in_full[slot], 16u * SUB_BYTES);
+          uint8_t* dst = inring + (size_t)slot * DW_STAGE;
+          for (int sl = 0; sl < 2; ++sl) {
+            const int zin = 2 * (z0 + j) + sl - a.pad + a.shift[0];
+            for (int rr = 0; rr < 4; ++rr) {
+              const int ry = rr >> 1, rx = rr & 1;
+              const int mly = (((ry + a.pad) & 1) - a.pad - ry) / 2, mlx = (((rx + a.pad) & 1) - a.pad - rx) / 2;
+              const int cy = 2 * (y0 + mly) + ry + a.shift[1], cx = 2 * (x0 + mlx) + rx + a.shift[2];
+              for (int p = 0; p < 2; ++p)
+                tma_load_5d(dst + ((sl * 4 + rr) * 2 + p) * SUB_STRIDE, &map0, &in_full[slot], (2 * c + p) * 8, cx, cy, zin, b);
+            }
+          }
+        }
+        __syncwarp();
+        if (++slot == DW_NIN) { slot = 0; ph ^= 1u; }
+      }
+  } else if (warp == 10) {
+    int slot = 0; uint32_t ph = 0;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nch * 64 * wstage;
+    for (int c = 0; c < nch; ++c)
+      for (int j = 0; j <= nz; ++j)
+        for (int h = 0; h < 2; ++h) {
+          const int zo = j - h;
+          if (zo < 0 || zo >= nz) continue;
+          const uint8_t* src = wsrc + (size_t)(c * 64 + h * 32) * wstage;       // stage order = MMA order: kz, parity, my, mx
+          for (int i = 0; i < 32; ++i) {
+            mbar_wait(&w_empty[slot], ph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&w_full[slot], (uint32_t)wstage);
+              bulk_load(wring + (size_t)slot * wstage, src + (size_t)i * wstage, (uint32_t)wstage, &w_full[slot]);
+            }
+            __syncwarp();
+            if (++slot == nw) { slot = 0; ph ^= 1u; }
+          }
+        }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = ((uint32_t)SUB_STRIDE >> 4) << 16;            // K halves = the two planes of the chunk
+    const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;
+    const uint32_t in16 = smem_u32(inring) >> 4, w16 = smem_u32(wring) >> 4;
+    const uint32_t wst16 = (uint32_t)wstage >> 4;
+    int islot = 0; uint32_t iph = 0; int wslot = 0; uint32_t wph = 0;
+    for (int c = 0; c < nch; ++c)
+      for (int j = 0; j <= nz; ++j) {
+        mbar_wait(&in_full[islot], iph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ib16 = in16 + (uint32_t)islot * (DW_STAGE >> 4);
+        for (int h = 0; h < 2; ++h) {
+          const int zo = j - h;
+          if (zo < 0 || zo >= nz) continue;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(zo * NP);
+          uint32_t acc = (c == 0 && h == 0) ? 0u : 1u;
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i) {                  // i = (sl, parity, my, mx)
+            mbar_wait(&w_full[wslot], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t alo = (ib16 + (uint32_t)((((i >> 2) * 2) * SUB_STRIDE) >> 4) + (uint32_t)(((i >> 1) & 1) * SXV + (i & 1))) | a_lbo;
+              const uint32_t blo = (w16 + (uint32_t)wslot * wst16) | b_lbo;
+              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+              umma_commit(&w_empty[wslot]);
+            }
+            __syncwarp();
+            acc = 1u;
+            if (++wslot == nw) { wslot = 0; wph ^= 1u; }
+          }
+          if (c == nch - 1 && h == 1) {                   // output slice zo has received all four kz taps of the last chunk
+            if (elect_one()) umma_commit(&tfull_bar[zo]);
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit(&in_empty[islot]);
+        __syncwarp();
+        if (++islot == DW_NIN) { islot = 0; iph ^= 1u; }
+      }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                    // column half handled by this warp
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int oy = y0 + yl, ox = x0 + xl;
+    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const int cbeg = half * (NP >> 1), cend = cbeg + (NP >> 1);
+    for (int zo = 0; zo < nz; ++zo) {
+      const int oz = z0 + zo;
+      mbar_wait(&tfull_bar[zo], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * NP);
+      for (int cb = cbeg; cb < cend; cb += 32) {
+        __syncwarp();
+        uint4 refq[4], accq[4];
+        if (inside) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (co0 + cb + c * 8 < a.Cout) {
+              if (a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0 + cb + c * 8));
+              if (a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + co0 + cb + c * 8);
+            }
+          }
+        }
+        uint32_t r[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) tmem_ld8(taddr + (uint32_t)(cb + c), r + c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (inside) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (co0 + cb + c * 8 < a.Cout) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
+              Epi::run(a, v, co0 + cb + c * 8, b, oz, oy, ox, refq[c], accq[c]);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// weight stages of the wide DOWN kernel: [cout group][chunk][kz][parity (ry,rx)][my][mx][k-half][n-group (NP/8)][8][8]
+struct PackDwArgs { const float* w; long long ws_tap, ws_in, ws_out; int nch, cout, np, pad; bf16* dst; long long total; };
+__global__ void pack_weights_dw_kernel(const PackDwArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  long long t = i;
+  const int e = (int)(t & 7); t >>= 3;
+  const int r = (int)(t & 7); t >>= 3;
+  const int ng = a.np >> 3;
+  const int g = (int)(t % ng); t /= ng;
+  const int j = (int)(t & 1); t >>= 1;
+  const int mx = (int)(t & 1); t >>= 1;
+  const int my = (int)(t & 1); t >>= 1;
+  const int rr = (int)(t & 3); t >>= 2;
+  const int kz = (int)(t & 3); t >>= 2;
+  const int c = (int)(t % a.nch); t /= a.nch;
+  const int cg = (int)t;
+  const int ry = rr >> 1, rx = rr & 1;
+  const int ky = ((ry + a.pad) & 1) + 2 * my, kx = ((rx + a.pad) & 1) + 2 * mx;
+  const int co = cg * a.np + g * 8 + r, ci = c * 16 + j * 8 + e;
+  float v = 0.f;
+  if (co < a.cout) v = a.w[(long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)ci * a.ws_in + (long long)co * a.ws_out];
+  a.dst[i] = __float2bfloat16_rn(v);
+}
+
+int dw_np(int cout) { const int n = (cout + 63) / 64 * 64; return n > 256 ? 256 : n; }
+
 // bf16 UMMA B image [step][k-half][n-group][8 rows][8 elems]; the step order is the issue order of the kernels above
 struct PackS2Args {
   const float* w; long long ws_tap, ws_in, ws_out;
@@ -476,9 +881,13 @@ int steps_of(const ConvArgs& a) {
   const int per_yz = (cin == 8) ? 1 : 2 * (cin / 16);
   return (a.form == 1) ? 4 * per_yz : 32 * per_yz;
 }
+size_t resident_packed_bytes(const ConvArgs& a) {
+  const int np = (a.form == 1) ? 8 * cp_of(a.Cout) : npad_of(a.Cout);
+  return (size_t)steps_of(a) * np * 32;
+}
 int ring_of(const ConvArgs& a, size_t& smem_out) {
   const int cin = a.C0;
-  const size_t wb = (tc_s2_packed_bytes(a) + 1023) & ~(size_t)1023;
+  const size_t wb = (resident_packed_bytes(a) + 1023) & ~(size_t)1023;
   const size_t slot = (size_t)(a.form == 1 ? 1 : 4) * (cin / 8) * SUB_STRIDE;
   const int want = (a.form == 1) ? 6 : 8, least = (a.form == 1) ? 3 : 5;
   int ring = want;
@@ -486,12 +895,30 @@ int ring_of(const ConvArgs& a, size_t& smem_out) {
   smem_out = wb + ring * slot + 1024;
   return ring;
 }
+// 0: resident-weight kernels (conv_up_tc / conv_down_tc), 1: wide UP, 2: wide DOWN, -1: shape not covered
+int variant_of(const ConvArgs& a) {
+  const int cin = a.C0;
+  if ((cin == 8 || (cin % 16 == 0 && cin <= 64)) && a.Cout <= 32) {
+    size_t smem; ring_of(a, smem);
+    if (smem <= 200 * 1024) return 0;
+  }
+  if (a.form == 1 && cin >= 64 && cin % 64 == 0) return 1;
+  if (a.form == 0 && cin >= 16 && cin % 16 == 0 && (a.Cout > 32 || cin > 64)) return 2;   // 32 -> 32 stays on conv_mma.cu
+  return -1;
+}
 
 }  // namespace
 
 size_t tc_s2_packed_bytes(const ConvArgs& a) {
-  const int np = (a.form == 1) ? 8 * cp_of(a.Cout) : npad_of(a.Cout);
-  return (size_t)steps_of(a) * np * 32;
+  const int v = variant_of(a);
+  if (v == 1) return (size_t)((a.Cout + 31) / 32) * (a.C0 / 64) * 32 * UW_WSTAGE;
+  if (v == 2) { const int np = dw_np(a.Cout); return (size_t)((a.Cout + np - 1) / np) * (a.C0 / 16) * 64 * np * 32; }
+  return resident_packed_bytes(a);
+}
+
+const char* tc_s2_kernel_name(const ConvArgs& a) {
+  const int v = variant_of(a);
+  return v == 1 ? "conv_upw_tc_kernel" : v == 2 ? "conv_downw_tc_kernel" : (a.form == 1 ? "conv_up_tc_kernel" : "conv_down_tc_kernel");
 }
 
 bool tc_s2_supported(const ConvArgs& a) {
@@ -500,22 +927,32 @@ bool tc_s2_supported(const ConvArgs& a) {
   if (a.form != 0 && a.form != 1) return false;
   if (a.s0.dtype != DT_BF16 || a.out_dtype != DT_BF16) return false;
   if (a.s0.origins || a.use_lut || a.bias || a.C1) return false;
-  const int cin = a.C0;
-  if (!(cin == 8 || (cin % 16 == 0 && cin <= 64))) return false;
-  if (a.s0.C != cin || a.s0.coff != 0) return false;
-  if (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8) return false;
+  if (a.s0.C != a.C0 || a.s0.coff != 0) return false;
+  if (a.Cout % 8 || a.out_C % 8 || a.out_coff % 8) return false;
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
-  size_t smem; ring_of(a, smem);
-  if (smem > 200 * 1024) return false;
+  if (variant_of(a) < 0) return false;
   return tem_get_encode() != nullptr;
 }
 
 cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  const int v = variant_of(a);
+  if (v == 1) {
+    PackUpwArgs q; q.w = a.w; q.ws_tap = a.ws_tap; q.ws_in = a.ws_in; q.ws_out = a.ws_out;
+    q.nchunks = a.C0 / 64; q.cout = a.Cout; q.dst = dst; q.total = (long long)(tc_s2_packed_bytes(a) / 2);
+    pack_weights_upw_kernel<<<(unsigned)((q.total + 255) / 256), 256, 0, st>>>(q); ++g_tem_launches;
+    return cudaGetLastError();
+  }
+  if (v == 2) {
+    PackDwArgs q; q.w = a.w; q.ws_tap = a.ws_tap; q.ws_in = a.ws_in; q.ws_out = a.ws_out;
+    q.nch = a.C0 / 16; q.cout = a.Cout; q.np = dw_np(a.Cout); q.pad = a.pad[0]; q.dst = dst; q.total = (long long)(tc_s2_packed_bytes(a) / 2);
+    pack_weights_dw_kernel<<<(unsigned)((q.total + 255) / 256), 256, 0, st>>>(q); ++g_tem_launches;
+    return cudaGetLastError();
+  }
   PackS2Args p;
   p.w = a.w; p.ws_tap = a.ws_tap; p.ws_in = a.ws_in; p.ws_out = a.ws_out;
   p.up = a.form == 1; p.pad = a.pad[0]; p.cin = a.C0; p.cols = a.Cout; p.cp = cp_of(a.Cout);
   p.np = p.up ? 8 * p.cp : npad_of(a.Cout); p.cin8 = a.C0 == 8;
-  p.dst = dst; p.total = (int)(tc_s2_packed_bytes(a) / 2);
+  p.dst = dst; p.total = (int)(resident_packed_bytes(a) / 2);
   pack_weights_s2_kernel<<<(p.total + 255) / 256, 256, 0, st>>>(p); ++g_tem_launches;
   return cudaGetLastError();
 }
@@ -534,10 +971,23 @@ static bool make_map_s2(CUtensorMap* m, const void* base, int B, int Z, int Y, i
   return r == CUDA_SUCCESS;
 }
 
+// z chunking of the wide kernels (one CTA per SM): fewest waves x (slices per CTA + fixed cost)
+static void pick_chunks(long long ctas_per_z, int q0, int zmax, int fixed, int& zc, int& nzc) {
+  double best = 1e30; zc = zmax < q0 ? zmax : q0; 
+  for (int cand = 1; cand <= zmax && cand <= q0; ++cand) {
+    const int n = (q0 + cand - 1) / cand;
+    const long long waves = (ctas_per_z * n + 147) / 148;
+    const double cost = (double)waves * (cand + fixed);
+    if (cost < best - 1e-9 || (cost < best + 1e-9 && cand > zc)) { best = cost; zc = cand; }
+  }
+  nzc = (q0 + zc - 1) / zc;
+}
+
 cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st) {
   S2Args t; memset(&t, 0, sizeof(t));
   const int cin = a.C0;
   const bool up = a.form == 1;
+  const int variant = variant_of(a);
   t.B = a.B; t.pad = a.pad[0];
   for (int i = 0; i < 3; ++i) {
     t.L[i] = a.L[i]; t.shift[i] = a.s0.shift[i];
@@ -548,6 +998,35 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   t.wpacked = wpacked; t.wbytes = (int)tc_s2_packed_bytes(a);
   t.ntx = (t.Q[2] + TX - 1) / TX; t.nty = (t.Q[1] + TY - 1) / TY;
   const long long cols = (long long)a.B * t.ntx * t.nty;
+  t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
+  t.Cout = a.Cout; t.slope = a.slope;
+  t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
+  t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  CUtensorMap m0;
+  if (variant == 1) {
+    if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue;
+    const int groups = (a.Cout + 31) / 32;
+    pick_chunks(cols * groups, t.Q[0], 1 << 20, 1, t.zc, t.nzc);
+    const size_t smem = (size_t)UW_NIN * UW_IN_STAGE + (size_t)UW_NW * UW_WSTAGE + 1024;
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv_upw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }
+    conv_upw_tc_kernel<<<dim3((unsigned)(cols * t.nzc), (unsigned)groups), kThreadsUpw, smem, st>>>(m0, t);
+    ++g_tem_launches;
+    return cudaGetLastError();
+  }
+  if (variant == 2) {
+    if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
+    t.np = dw_np(a.Cout);
+    const int groups = (a.Cout + t.np - 1) / t.np;
+    t.ring = DW_WRING / (t.np * 32); if (t.ring > DW_WMAX) t.ring = DW_WMAX;
+    pick_chunks(cols * groups, t.Q[0], 512 / t.np, 1, t.zc, t.nzc);
+    const size_t smem = (size_t)DW_NIN * DW_STAGE + (size_t)DW_WRING + 1024;
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv_downw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }
+    conv_downw_tc_kernel<<<dim3((unsigned)(cols * t.nzc), (unsigned)groups), kThreadsDw, smem, st>>>(m0, t);
+    ++g_tem_launches;
+    return cudaGetLastError();
+  }
   size_t smem; t.ring = ring_of(a, smem);
   // z chunks: as many CTAs as are resident at once (one wave), chunks of at least two slices
   const int tmem_cols = up ? 16 * cp_of(a.Cout) : 2 * npad_of(a.Cout);
@@ -561,11 +1040,6 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   if (nzc > (t.Q[0] + 1) / 2) nzc = (t.Q[0] + 1) / 2;
   if (nzc < 1) nzc = 1;
   t.zc = (t.Q[0] + nzc - 1) / nzc; t.nzc = (t.Q[0] + t.zc - 1) / t.zc;
-  t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
-  t.Cout = a.Cout; t.slope = a.slope;
-  t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
-  t.drop_key = a.drop_key; t.accumulate = a.accumulate;
-  CUtensorMap m0;
   if (up) { if (!tem_make_map_plane(&m0, &t.merged, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue; }
   else if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)(cols * t.nzc);

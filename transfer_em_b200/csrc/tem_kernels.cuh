@@ -123,6 +123,7 @@ bool tc_s2_supported(const ConvArgs& a);
 size_t tc_s2_packed_bytes(const ConvArgs& a);
 cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
+const char* tc_s2_kernel_name(const ConvArgs& a);   // resident-weight or wide (streamed-weight) variant chosen for the shape
 
 // conv_small.cu: strided 4x4x4 forward for small output volumes with K = 64*Cin (d4, d6)
 bool conv_small_supported(const ConvArgs& a);

@@ -29,6 +29,7 @@ extern "C" int tem_abi_version(void) { return TEM_ABI_VERSION; }
 unsigned long long g_tem_launches = 0;
 const char* g_tem_last_kernel = "?";
 extern "C" uint64_t tem_launch_count(void) { return g_tem_launches; }
+extern "C" const char* tem_last_kernel(void) { return g_tem_last_kernel; }
 
 static cudaEvent_t prof_event(Profiler& p) {
   if (p.used == p.pool.size()) { cudaEvent_t e; cudaEventCreate(&e); p.pool.push_back(e); }
@@ -184,7 +185,7 @@ static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaS
   return kind == 2 ? tc_s2_pack_weights(a, dst, st) : (kind == 1 ? tc_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st));
 }
 static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
-  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? (a.form == 1 ? "conv_up_tc_kernel" : "conv_down_tc_kernel") : kind == 1 ? "conv3_tc_kernel" : "conv3_tc3_kernel";
+  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? tc_s2_kernel_name(a) : kind == 1 ? "conv3_tc_kernel" : "conv3_tc3_kernel";
   if (kind == 3) return launch_conv_tcw(a, wp, st);
   return kind == 2 ? launch_conv_tc_s2(a, wp, st) : (kind == 1 ? launch_conv_tc(a, wp, st) : launch_conv_tc3(a, wp, st));
 }
