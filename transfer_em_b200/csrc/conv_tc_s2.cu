@@ -45,7 +45,7 @@ struct S2Args {
   int shift[3];                // tensor coordinate = conv-input coordinate + shift
   int cin8;
   const bf16* wpacked; int wbytes;
-  int ntx, nty, nzc, zc, ring;      // ring: input slots (resident-weight kernels) / weight slots (wide DOWN)
+  int ntx, nty, nzc, zc, ring;      // ring: input slots (resident-weight kernels) / K-steps per weight stage (wide DOWN)
   int np;                            // wide DOWN: MMA N (columns per output slice)
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
@@ -434,14 +434,15 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 // 32 output channels = 256 columns, blockIdx.y = group of 32 output channels), but K = 8 taps x Cin no longer fits in
 // shared memory as weights (Cin = 64 already needs 256 KB), so BOTH operands are streamed:
 //   * inputs: per q-slice and 64-channel chunk, the two source slices (qz-1, qz) of that chunk (40 KB stage, 2 stages);
-//   * weights: one K-step (16 channels x 256 columns = 8 KB) per stage through a 12-stage ring, in MMA order.
+//   * weights: two K-steps (2 x 16 channels x 256 columns = 16 KB) per stage through a 6-stage ring, in MMA order.
 // Two producer warps (inputs / weights), one MMA issuer, eight epilogue warps.
 // ------------------------------------------------------------------------------------------------
 constexpr int UW_PL = 8;                                 // planes (64 channels) per input chunk
 constexpr int UW_IN_STAGE = 2 * UW_PL * SUB_STRIDE;      // 40960
 constexpr int UW_NIN = 2;
-constexpr int UW_WSTAGE = 256 * 32;                      // 8192 B: [k-half][32 n-groups][8][8] bf16
-constexpr int UW_NW = 12;
+constexpr int UW_KSTEP = 256 * 32;                       // 8192 B: one K-step [k-half][32 n-groups][8][8] bf16
+constexpr int UW_WSTAGE = 2 * UW_KSTEP;                  // two K-steps per ring slot: one barrier round trip per 256 tensor cycles
+constexpr int UW_NW = 6;
 constexpr int kThreadsUpw = 352;                         // warps: 0 input TMA, 1 MMA, 2-9 epilogue, 10 weight loads
 
 __global__ void __launch_bounds__(kThreadsUpw, 1)
@@ -490,9 +491,9 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       }
   } else if (warp == 10) {
     int slot = 0; uint32_t ph = 0;
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nchunks * 32 * UW_WSTAGE;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nchunks * 32 * UW_KSTEP;
     for (int zo = 0; zo < nz; ++zo)
-      for (int st = 0; st < nchunks * 32; ++st) {       // stage order = MMA order: chunk, tap (mz,my,mx), 16-channel step
+      for (int st = 0; st < nchunks * 16; ++st) {       // stage order = MMA order: chunk, tap (mz,my,mx), pair of 16-channel steps
         mbar_wait(&w_empty[slot], ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&w_full[slot], (uint32_t)UW_WSTAGE);
@@ -520,13 +521,17 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         for (int tap = 0; tap < 8; ++tap) {
           const int mz = tap >> 2, my = (tap >> 1) & 1, mx = tap & 1;
 #pragma unroll 1
-          for (int kc = 0; kc < UW_PL / 2; ++kc) {
+          for (int kp = 0; kp < UW_PL / 4; ++kp) {
             mbar_wait(&w_full[wslot], wph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-              const uint32_t alo = (ib16 + (uint32_t)(((mz * UW_PL + 2 * kc) * SUB_STRIDE) >> 4) + (uint32_t)(my * SXV + mx)) | a_lbo;
-              const uint32_t blo = (w16 + (uint32_t)wslot * (UW_WSTAGE >> 4)) | b_lbo;
-              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int kc = 2 * kp + k2;
+                const uint32_t alo = (ib16 + (uint32_t)(((mz * UW_PL + 2 * kc) * SUB_STRIDE) >> 4) + (uint32_t)(my * SXV + mx)) | a_lbo;
+                const uint32_t blo = (w16 + (uint32_t)wslot * (UW_WSTAGE >> 4) + (uint32_t)(k2 * (UW_KSTEP >> 4))) | b_lbo;
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, (k2 == 0) ? acc : 1u);
+              }
               umma_commit(&w_empty[wslot]);
             }
             __syncwarp();
@@ -632,13 +637,13 @@ __global__ void pack_weights_upw_kernel(const PackUpwArgs a) {
 // pair (2j, 2j+1) of a chunk is staged ONCE and feeds both output slices that read it (zo = j with kz = 0,1 and
 // zo = j - 1 with kz = 2,3).  Weights are streamed in MMA order, one K-step (16 x NP) per ring slot.
 //   input stage : [slice 2][parity (ry,rx) 4][plane 2] de-interleaved sub-tiles = 40 KB, 3 stages
-//   weight stage: NP x 32 B, ring of 80 KB
+//   weight stage: KS = 8 / 4 / 2 K-steps of NP x 32 B (NP = 64 / 128 / 256), six 16 KB slots
 // Warps: 0 input TMA, 1 MMA issuer, 2-9 epilogue (two per TMEM lane quadrant, half of the columns each), 10 weights.
 // ------------------------------------------------------------------------------------------------
 constexpr int DW_STAGE = 16 * SUB_STRIDE;                // 40960
 constexpr int DW_NIN = 3;
-constexpr int DW_WRING = 80 * 1024;
-constexpr int DW_WMAX = 40;                              // slots at NP = 64
+constexpr int DW_WSLOT = 16 * 1024;                      // one ring slot = KS K-steps (KS x NP x 32 B <= 16 KB): 256 tensor cycles per barrier round trip
+constexpr int DW_WMAX = 6;
 constexpr int kThreadsDw = 352;
 constexpr int DW_ZMAX = 8;                               // output slices per CTA at NP = 64
 
@@ -651,8 +656,9 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
   uint8_t* inring = smem;
   uint8_t* wring = smem + DW_NIN * DW_STAGE;
   const int NP = a.np;
-  const int wstage = NP * 32;
-  const int nw = a.ring;                                 // weight slots
+  const int KS = a.ring;                                 // K-steps per weight stage
+  const int wstage = KS * NP * 32;
+  const int nst = 32 / KS;                               // stages per (chunk, kz pair)
   const int cg = blockIdx.y, co0 = cg * NP;
   const int nch = a.planes >> 1;                         // 16-channel chunks
 
@@ -660,7 +666,7 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < DW_NIN; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
-    for (int i = 0; i < nw; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < DW_WMAX; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < DW_ZMAX; ++i) mbar_init(&tfull_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -697,21 +703,21 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       }
   } else if (warp == 10) {
     int slot = 0; uint32_t ph = 0;
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nch * 64 * wstage;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nch * 64 * (NP * 32);
     for (int c = 0; c < nch; ++c)
       for (int j = 0; j <= nz; ++j)
         for (int h = 0; h < 2; ++h) {
           const int zo = j - h;
           if (zo < 0 || zo >= nz) continue;
-          const uint8_t* src = wsrc + (size_t)(c * 64 + h * 32) * wstage;       // stage order = MMA order: kz, parity, my, mx
-          for (int i = 0; i < 32; ++i) {
+          const uint8_t* src = wsrc + (size_t)(c * 64 + h * 32) * (NP * 32);    // K-step order = MMA order: kz, parity, my, mx
+          for (int i = 0; i < nst; ++i) {
             mbar_wait(&w_empty[slot], ph ^ 1u);
             if (elect_one()) {
               mbar_arrive_expect_tx(&w_full[slot], (uint32_t)wstage);
-              bulk_load(wring + (size_t)slot * wstage, src + (size_t)i * wstage, (uint32_t)wstage, &w_full[slot]);
+              bulk_load(wring + (size_t)slot * DW_WSLOT, src + (size_t)i * wstage, (uint32_t)wstage, &w_full[slot]);
             }
             __syncwarp();
-            if (++slot == nw) { slot = 0; ph ^= 1u; }
+            if (++slot == DW_WMAX) { slot = 0; ph ^= 1u; }
           }
         }
   } else if (warp == 1) {
@@ -720,7 +726,7 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const uint32_t a_lbo = ((uint32_t)SUB_STRIDE >> 4) << 16;            // K halves = the two planes of the chunk
     const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;
     const uint32_t in16 = smem_u32(inring) >> 4, w16 = smem_u32(wring) >> 4;
-    const uint32_t wst16 = (uint32_t)wstage >> 4;
+    const uint32_t kst16 = (uint32_t)(NP * 32) >> 4;
     int islot = 0; uint32_t iph = 0; int wslot = 0; uint32_t wph = 0;
     for (int c = 0; c < nch; ++c)
       for (int j = 0; j <= nz; ++j) {
@@ -733,18 +739,23 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(zo * NP);
           uint32_t acc = (c == 0 && h == 0) ? 0u : 1u;
 #pragma unroll 1
-          for (int i = 0; i < 32; ++i) {                  // i = (sl, parity, my, mx)
+          for (int st = 0; st < nst; ++st) {
             mbar_wait(&w_full[wslot], wph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-              const uint32_t alo = (ib16 + (uint32_t)((((i >> 2) * 2) * SUB_STRIDE) >> 4) + (uint32_t)(((i >> 1) & 1) * SXV + (i & 1))) | a_lbo;
-              const uint32_t blo = (w16 + (uint32_t)wslot * wst16) | b_lbo;
-              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, acc);
+              const uint32_t wb16 = w16 + (uint32_t)wslot * (DW_WSLOT >> 4);
+#pragma unroll 2
+              for (int k = 0; k < KS; ++k) {
+                const int i = st * KS + k;                // i = (sl, parity, my, mx)
+                const uint32_t alo = (ib16 + (uint32_t)((((i >> 2) * 2) * SUB_STRIDE) >> 4) + (uint32_t)(((i >> 1) & 1) * SXV + (i & 1))) | a_lbo;
+                const uint32_t blo = (wb16 + (uint32_t)k * kst16) | b_lbo;
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, (k == 0) ? acc : 1u);
+              }
               umma_commit(&w_empty[wslot]);
             }
             __syncwarp();
             acc = 1u;
-            if (++wslot == nw) { wslot = 0; wph ^= 1u; }
+            if (++wslot == DW_WMAX) { wslot = 0; wph ^= 1u; }
           }
           if (c == nch - 1 && h == 1) {                   // output slice zo has received all four kz taps of the last chunk
             if (elect_one()) umma_commit(&tfull_bar[zo]);
@@ -911,7 +922,7 @@ int variant_of(const ConvArgs& a) {
 
 size_t tc_s2_packed_bytes(const ConvArgs& a) {
   const int v = variant_of(a);
-  if (v == 1) return (size_t)((a.Cout + 31) / 32) * (a.C0 / 64) * 32 * UW_WSTAGE;
+  if (v == 1) return (size_t)((a.Cout + 31) / 32) * (a.C0 / 64) * 32 * UW_KSTEP;
   if (v == 2) { const int np = dw_np(a.Cout); return (size_t)((a.Cout + np - 1) / np) * (a.C0 / 16) * 64 * np * 32; }
   return resident_packed_bytes(a);
 }
@@ -1018,9 +1029,9 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
     if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
     t.np = dw_np(a.Cout);
     const int groups = (a.Cout + t.np - 1) / t.np;
-    t.ring = DW_WRING / (t.np * 32); if (t.ring > DW_WMAX) t.ring = DW_WMAX;
+    t.ring = t.np <= 64 ? 8 : (t.np <= 128 ? 4 : 2);          // K-steps per weight stage
     pick_chunks(cols * groups, t.Q[0], 512 / t.np, 1, t.zc, t.nzc);
-    const size_t smem = (size_t)DW_NIN * DW_STAGE + (size_t)DW_WRING + 1024;
+    const size_t smem = (size_t)DW_NIN * DW_STAGE + (size_t)DW_WMAX * DW_WSLOT + 1024;
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv_downw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }
     conv_downw_tc_kernel<<<dim3((unsigned)(cols * t.nzc), (unsigned)groups), kThreadsDw, smem, st>>>(m0, t);
