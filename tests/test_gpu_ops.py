@@ -440,6 +440,44 @@ def test_single_channel_conv_fast_paths():
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 
 
+def test_single_channel_conv_wide_models():
+    """The single-channel ends of the wf <= 4 models (g0 / d0: 1 -> 64, g11: 128 -> 1) stay on the dedicated kernels:
+    the channel dimension is sliced into 16-channel (1 -> C) / 32-channel (C -> 1) launches."""
+    lib = _lib.load()
+    r = np.random.default_rng(654)
+    B, dims = 2, (7, 11, 35)
+    u = r.integers(0, 256, (B,) + dims + (1,), dtype=np.uint8)
+    ms = (0.05, 0.6)
+    xs = O.standardize_population(O.scale_tensor(u[..., 0]), ms).astype(np.float64)
+    w = bf16r(r.standard_normal((3, 3, 3, 1, 64)) * 0.3)
+    d = make_desc(B, dims, 1, 64, 3, 1, False, 0.3, 0, torch.uint8, torch.bfloat16, ms, tc=1)
+    y = conv_forward(torch.tensor(u).to(DEV), _cuda(w, torch.float32), d).float().cpu().numpy()
+    assert lib.tem_last_kernel().decode() == "conv_c1_kernel"
+    ref = naive.lrelu(naive.conv_fwd(xs, w, 1), 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+    # data gradient of the 1 -> 64 layer into its fp32 single-channel input (64 -> 1, flipped taps, zero padding 2)
+    dy = bf16r(r.standard_normal(ref.shape))
+    df = make_desc(B, dims, 1, 64, 3, 1, False, 0.3, 0, torch.float32, torch.bfloat16, tc=1)
+    dx = conv_dgrad(_cuda(dy, torch.bfloat16), _cuda(w, torch.float32), df, None, 1.0, torch.float32).cpu().numpy()
+    assert lib.tem_last_kernel().decode() == "conv_c1_kernel"
+    dref = naive.conv_dgrad(dy, w, 1, xs.shape)
+    np.testing.assert_allclose(dx, dref, rtol=1e-3, atol=1e-3)
+    # 128 -> 1 forward (fp32, linear) and its data gradient (1 -> 128 with LeakyReLU' of the stored activation)
+    x = bf16r(r.standard_normal((B,) + dims + (128,)))
+    w1 = bf16r(r.standard_normal((3, 3, 3, 128, 1)) * 0.1)
+    d1 = make_desc(B, dims, 128, 1, 3, 1, False, 1.0, 0, torch.bfloat16, torch.float32, tc=1)
+    y1 = conv_forward(_cuda(x, torch.bfloat16), _cuda(w1, torch.float32), d1).cpu().numpy()
+    assert lib.tem_last_kernel().decode() == "conv_c1_kernel"
+    ref1 = naive.conv_fwd(x, w1, 1)
+    np.testing.assert_allclose(y1, ref1, rtol=1e-4, atol=2e-4)
+    dy1 = r.standard_normal(ref1.shape).astype(np.float32)
+    act = bf16r(r.standard_normal(x.shape))
+    dx1 = conv_dgrad(torch.tensor(dy1).to(DEV), _cuda(w1, torch.float32), d1, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
+    assert lib.tem_last_kernel().decode() == "conv_c1_kernel"
+    dref1 = naive.conv_dgrad(dy1.astype(np.float64), w1, 1, x.shape) * naive.lrelu_grad_from_output(act, 0.3)
+    np.testing.assert_allclose(dx1, dref1, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
+
+
 def test_tma_wgrad_variant_in_subprocess():
     """The opt-in TMA-ring weight-gradient kernel (TEM_WGRAD_TMA=1) must agree with the oracle too."""
     import os, subprocess, sys

@@ -350,10 +350,13 @@ bool conv_c1_supported(const ConvArgs& a) {
   if (a.C1 != 0 || a.bias) return false;
   for (int i = 0; i < 3; ++i) if (a.k[i] != 3 || a.stride[i] != 1) return false;
   const bool plain = !a.accumulate && !a.conv_off[0] && !a.conv_off[1] && !a.conv_off[2];
-  if (plain && a.C0 == 1 && (a.Cout == 8 || a.Cout == 16) && a.out_dtype == DT_BF16 && a.out_C % 8 == 0 && a.out_coff % 8 == 0 &&
+  // wide models (wf <= 4): the channel dimension is cut into slices of 16 (1 -> C) / 32 (C -> 1) handled by one launch each
+  const bool co_ok = a.Cout == 8 || a.Cout == 16 || (a.Cout % 16 == 0 && !a.drop_key);
+  const bool ci_ok = a.C0 == 8 || a.C0 == 16 || a.C0 == 32 || (a.C0 % 32 == 0 && a.slope == 1.f);
+  if (plain && a.C0 == 1 && co_ok && a.out_dtype == DT_BF16 && a.out_C % 8 == 0 && a.out_coff % 8 == 0 &&
       (!a.ref || (a.ref_C % 8 == 0 && a.ref_coff % 8 == 0)))
     return true;                                                     // 1 -> C (form 0 forward, form 1 = flipped + pad 2)
-  if ((a.form == 0 ? plain : true) && a.Cout == 1 && a.out_dtype == DT_F32 && a.s0.dtype == DT_BF16 && (a.C0 == 8 || a.C0 == 16 || a.C0 == 32) &&
+  if ((a.form == 0 ? plain : true) && a.Cout == 1 && a.out_dtype == DT_F32 && a.s0.dtype == DT_BF16 && ci_ok &&
       a.s0.C % 8 == 0 && a.s0.coff % 8 == 0 && !a.s0.origins && !a.ref && !a.drop_key)
     return true;                                                     // C -> 1 forward; form 1 = data gradient of a 1 -> C layer
   return false;
@@ -363,6 +366,24 @@ cudaError_t launch_conv_c1(const ConvArgs& a, cudaStream_t st) {
   const int ntx = (a.L[2] + TXT - 1) / TXT, nty = (a.L[1] + TY - 1) / TY, ntz = (a.L[0] + TZ - 1) / TZ;
   const long long grid = (long long)a.B * ntx * nty * ntz;
   if (grid == 0) return cudaSuccess;
+  if (a.C0 == 1 && a.Cout > 16) {                  // 1 -> C, wide: one launch per 16 output channels (a 32 B sector per voxel)
+    for (int co0 = 0; co0 < a.Cout; co0 += 16) {
+      ConvArgs s = a;
+      s.Cout = 16; s.w = a.w + (long long)co0 * a.ws_out; s.out_coff = a.out_coff + co0; s.ref_coff = a.ref_coff + co0;
+      const cudaError_t e = launch_conv_c1(s, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  if (a.Cout == 1 && a.C0 > 32) {                  // C -> 1, wide (linear output): 32 input channels per launch, accumulated in fp32
+    for (int ci0 = 0; ci0 < a.C0; ci0 += 32) {
+      ConvArgs s = a;
+      s.C0 = 32; s.w = a.w + (long long)ci0 * a.ws_in; s.s0.coff = a.s0.coff + ci0; s.accumulate = a.accumulate || ci0 > 0;
+      const cudaError_t e = launch_conv_c1(s, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   if (c1in_v2_ok(a)) return launch_c1in_v2(a, st);
   if (a.C0 == 1) {
     if (a.Cout == 8) conv_c1in_kernel<8><<<(unsigned)grid, 256, 0, st>>>(a, ntx, nty, ntz, a.form == 1);

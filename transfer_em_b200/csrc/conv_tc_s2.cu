@@ -554,28 +554,49 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int yl = row >> 3, xl = row & 7;
     const int qy = y0 + yl, qx = x0 + xl;
     constexpr int NCH = CP / 8;
+    // Epilogue operands (LeakyReLU' reference, accumulate target) are the long-latency part of a q-slice: the lines of the
+    // NEXT q-slice are pulled into L2 while this one is processed, and the registers of class block c4 + 1 are loaded
+    // before block c4 is converted, so the TMEM stage is released after ~one L2 latency instead of four DRAM latencies.
+    auto coords = [&](int zo, int c4, int& oz, int& oy, int& ox) -> bool {
+      oz = 2 * (z0 + zo) + rz - a.pad; oy = 2 * qy + (c4 >> 1) - a.pad; ox = 2 * qx + (c4 & 1) - a.pad;
+      return zo < nz && oz >= 0 && oz < a.L[0] && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2];
+    };
+    auto prefetch_l2 = [&](int zo) {
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        int oz, oy, ox;
+        if (coords(zo, c4, oz, oy, ox) && co0 < a.Cout) {
+          if (a.ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0));
+          if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.out + Epi::out_off(a, b, oz, oy, ox) + co0));
+        }
+      }
+    };
+    auto fetch = [&](int zo, int c4, uint4* rq, uint4* aq) {
+      int oz, oy, ox;
+      if (coords(zo, c4, oz, oy, ox)) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (co0 + c * 8 < a.Cout) {
+            if (a.ref) rq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0 + c * 8));
+            if (a.accumulate) aq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + co0 + c * 8);
+          }
+        }
+      }
+    };
+    prefetch_l2(0);
+    uint4 refq[2][NCH], accq[2][NCH];
     for (int zo = 0; zo < nz; ++zo) {
-      const int qz = z0 + zo;
-      const int oz = 2 * qz + rz - a.pad;
-      const bool zok = oz >= 0 && oz < a.L[0];
+      prefetch_l2(zo + 1);
+      fetch(zo, 0, refq[0], accq[0]);
       mbar_wait(&tfull_bar[zo & 1], ((uint32_t)(zo >> 1)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo & 1) * NP + (uint32_t)(rz * 4 * CP);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         __syncwarp();
-        const int oy = 2 * qy + (c4 >> 1) - a.pad, ox = 2 * qx + (c4 & 1) - a.pad;
-        const bool ok = zok && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2];
-        uint4 refq[NCH], accq[NCH];
-        if (ok) {
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (co0 + c * 8 < a.Cout) {
-              if (a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0 + c * 8));
-              if (a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + co0 + c * 8);
-            }
-          }
-        }
+        if (c4 < 3) fetch(zo, c4 + 1, refq[(c4 + 1) & 1], accq[(c4 + 1) & 1]);
+        int oz, oy, ox;
+        const bool ok = coords(zo, c4, oz, oy, ox);
         uint32_t r[CP];
 #pragma unroll
         for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + (uint32_t)(c4 * CP + c), r + c);
@@ -591,7 +612,7 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              Epi::run(a, v, co0 + c * 8, b, oz, oy, ox, refq[c], accq[c]);
+              Epi::run(a, v, co0 + c * 8, b, oz, oy, ox, refq[c4 & 1][c], accq[c4 & 1][c]);
             }
           }
         }
@@ -774,6 +795,14 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int oy = y0 + yl, ox = x0 + xl;
     const bool inside = oy < a.L[1] && ox < a.L[2];
     const int cbeg = half * (NP >> 1), cend = cbeg + (NP >> 1);
+    if (inside && (a.ref || a.accumulate)) {            // epilogue operands of the whole strip into L2 while the MMAs run
+      for (int zo = 0; zo < nz; ++zo)
+        for (int cb = cbeg; cb < cend; cb += 32)
+          if (co0 + cb < a.Cout) {
+            if (a.ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ref + Epi::ref_off(a, b, z0 + zo, oy, ox) + co0 + cb));
+            if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.out + Epi::out_off(a, b, z0 + zo, oy, ox) + co0 + cb));
+          }
+    }
     for (int zo = 0; zo < nz; ++zo) {
       const int oz = z0 + zo;
       mbar_wait(&tfull_bar[zo], 0);
