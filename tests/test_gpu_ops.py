@@ -414,6 +414,20 @@ def test_tcgen05_stride2_dropout_epilogue():
     np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
 
 
+def test_wide_stride2_dropout_epilogue():
+    """Conv3DTranspose forward at 64 -> 32 channels (g6 at wf = 4) on conv_upw_tc_kernel with the fused Dropout(0.5) mask."""
+    key = 0x2345BCDE
+    r = np.random.default_rng(92)
+    x = bf16r(r.standard_normal((2, 5, 18, 9, 64)))
+    w = bf16r(r.standard_normal((4, 4, 4, 32, 64)) * 0.05)
+    d = make_desc(2, (5, 18, 9), 64, 32, 4, 2, True, 0.3, key, tc=1)
+    y = conv_forward(_cuda(x, torch.bfloat16), _cuda(w, torch.float32), d).float().cpu().numpy()
+    assert _lib.load().tem_last_kernel().decode() == "conv_upw_tc_kernel"
+    pre = naive.convT_fwd(x, w)
+    ref = naive.lrelu(pre * O.dropout_keep_mask(key, pre.shape) * 2.0, 0.3)
+    np.testing.assert_allclose(y, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
 def test_single_channel_conv_fast_paths():
     """1 -> C forward (uint8 / fp32), its flipped form (dgrad of a Cout=1 layer) and C -> 1 forward."""
     r = np.random.default_rng(321)

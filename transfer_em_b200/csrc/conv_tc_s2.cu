@@ -47,6 +47,8 @@ struct S2Args {
   const bf16* wpacked; int wbytes;
   int ntx, nty, nzc, zc, ring;      // ring: input slots (resident-weight kernels) / K-steps per weight stage (wide DOWN)
   int np;                            // wide DOWN: MMA N (columns per output slice)
+  int dbg;                           // experiment bits (TEM_S2_DBG): 1 no epilogue memory traffic, 2 no weight loads, 4 no input loads
+  int swz;                           // wide kernels: input tiles are [voxel][64 ch] rows in the 128B-swizzle layout (one TMA request per voxel)
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
   float slope;
@@ -87,7 +89,7 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
     }
     uint4 pk;
     pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(a.out + out_off(a, b, oz, oy, ox) + c0) = pk;
+    if (!(a.dbg & 32)) *reinterpret_cast<uint4*>(a.out + out_off(a, b, oz, oy, ox) + c0) = pk;
   }
 };
 
@@ -441,7 +443,7 @@ constexpr int UW_PL = 8;                                 // planes (64 channels)
 constexpr int UW_IN_STAGE = 2 * UW_PL * SUB_STRIDE;      // 40960
 constexpr int UW_NIN = 2;
 constexpr int UW_KSTEP = 256 * 32;                       // 8192 B: one K-step [k-half][32 n-groups][8][8] bf16
-constexpr int UW_WSTAGE = 2 * UW_KSTEP;                  // two K-steps per ring slot: one barrier round trip per 256 tensor cycles
+constexpr int UW_WRING = 96 * 1024;                      // weight ring: 6 slots of two K-steps (plane layout) / 3 slots of four (swizzled rows)
 constexpr int UW_NW = 6;
 constexpr int kThreadsUpw = 352;                         // warps: 0 input TMA, 1 MMA, 2-9 epilogue, 10 weight loads
 
@@ -456,6 +458,8 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
   uint8_t* wring = smem + UW_NIN * UW_IN_STAGE;
   const int cg = blockIdx.y, co0 = cg * CP;
   const int nchunks = a.planes / UW_PL;
+  const int kps = a.swz ? 4 : 2;                         // K-steps per weight stage
+  const int wstage = kps * UW_KSTEP, nw = UW_WRING / wstage;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < UW_NIN; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
@@ -480,11 +484,16 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&in_empty[slot], ph ^ 1u);
         if (elect_one()) {
+          if (a.dbg & 4) { mbar_arrive(&in_full[slot]); } else {
           mbar_arrive_expect_tx(&in_full[slot], (uint32_t)(2 * UW_PL) * SUB_BYTES);
           uint8_t* dst = inring + (size_t)slot * UW_IN_STAGE;
-          for (int sl = 0; sl < 2; ++sl)
-            for (int p = 0; p < UW_PL; ++p)
-              tma_load_5d(dst + (sl * UW_PL + p) * SUB_STRIDE, &map0, &in_full[slot], (c * UW_PL + p) * 8, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 + zo - 1 + sl + a.shift[0], b);
+          for (int sl = 0; sl < 2; ++sl) {
+            if (a.swz) tma_load_5d(dst + sl * (UW_PL * SUB_STRIDE), &map0, &in_full[slot], c * 64, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 + zo - 1 + sl + a.shift[0], b);
+            else
+              for (int p = 0; p < UW_PL; ++p)
+                tma_load_5d(dst + (sl * UW_PL + p) * SUB_STRIDE, &map0, &in_full[slot], (c * UW_PL + p) * 8, x0 - 1 + a.shift[2], y0 - 1 + a.shift[1], z0 + zo - 1 + sl + a.shift[0], b);
+          }
+          }
         }
         __syncwarp();
         if (++slot == UW_NIN) { slot = 0; ph ^= 1u; }
@@ -493,20 +502,29 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     int slot = 0; uint32_t ph = 0;
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpacked) + (size_t)cg * nchunks * 32 * UW_KSTEP;
     for (int zo = 0; zo < nz; ++zo)
-      for (int st = 0; st < nchunks * 16; ++st) {       // stage order = MMA order: chunk, tap (mz,my,mx), pair of 16-channel steps
+      for (int st = 0; st < nchunks * (32 / kps); ++st) {   // stage order = MMA order: chunk, tap (mz,my,mx), group of 16-channel steps
         mbar_wait(&w_empty[slot], ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)UW_WSTAGE);
-          bulk_load(wring + (size_t)slot * UW_WSTAGE, wsrc + (size_t)st * UW_WSTAGE, (uint32_t)UW_WSTAGE, &w_full[slot]);
+          if (a.dbg & 2) mbar_arrive(&w_full[slot]);
+          else {
+            mbar_arrive_expect_tx(&w_full[slot], (uint32_t)wstage);
+            bulk_load(wring + (size_t)slot * wstage, wsrc + (size_t)st * wstage, (uint32_t)wstage, &w_full[slot]);
+          }
         }
         __syncwarp();
-        if (++slot == UW_NW) { slot = 0; ph ^= 1u; }
+        if (++slot == nw) { slot = 0; ph ^= 1u; }
       }
   } else if (warp == 1) {
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lbo = ((uint32_t)SUB_STRIDE >> 4) << 16;            // K halves = two consecutive planes
-    const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;             // K halves of a weight stage
+    // A operand.  Plane layout: 8-channel planes, SBO = one tile row, LBO = next plane (K halves).  Swizzled layout: rows of
+    // 64 channels (128 B, SWIZZLE_128B as written by TMA), SBO = one tile row of 9 voxels, a K-step is 32 B further in the row;
+    // a tap is a start address shifted by whole rows (the swizzle XOR is a function of the shared-memory address).
+    const uint32_t a_hi = a.swz ? (((uint32_t)(SXV * 128) >> 4) | (1u << 14) | (2u << 29)) : (((uint32_t)ROW_B >> 4) | (1u << 14));
+    // B operand.  Plane layout: [k-half][n-group][8][8] per K-step.  Swizzled: 256 rows (n) of 64 input channels (128 B,
+    // chunk index XOR row & 7 done by the pack kernel), SBO = 1024 B, a K-step is 32 B further in the row.
+    const uint32_t b_hi = a.swz ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((128u >> 4) | (1u << 14));
+    const uint32_t a_lbo = a.swz ? (1u << 16) : (((uint32_t)SUB_STRIDE >> 4) << 16);
+    const uint32_t b_lbo = a.swz ? (1u << 16) : (((uint32_t)(NP * 16) >> 4) << 16);             // K halves of a weight stage
     const uint32_t in16 = smem_u32(inring) >> 4, w16 = smem_u32(wring) >> 4;
     int islot = 0; uint32_t iph = 0; int wslot = 0; uint32_t wph = 0;
     for (int zo = 0; zo < nz; ++zo) {
@@ -521,22 +539,24 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         for (int tap = 0; tap < 8; ++tap) {
           const int mz = tap >> 2, my = (tap >> 1) & 1, mx = tap & 1;
 #pragma unroll 1
-          for (int kp = 0; kp < UW_PL / 4; ++kp) {
+          for (int kp = 0; kp < 4 / kps; ++kp) {
             mbar_wait(&w_full[wslot], wph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-#pragma unroll
-              for (int k2 = 0; k2 < 2; ++k2) {
-                const int kc = 2 * kp + k2;
-                const uint32_t alo = (ib16 + (uint32_t)(((mz * UW_PL + 2 * kc) * SUB_STRIDE) >> 4) + (uint32_t)(my * SXV + mx)) | a_lbo;
-                const uint32_t blo = (w16 + (uint32_t)wslot * (UW_WSTAGE >> 4) + (uint32_t)(k2 * (UW_KSTEP >> 4))) | b_lbo;
+#pragma unroll 2
+              for (int k2 = 0; k2 < kps; ++k2) {
+                const int kc = kps * kp + k2;
+                const uint32_t aoff = a.swz ? (uint32_t)((mz * UW_PL * SUB_STRIDE) >> 4) + (uint32_t)((my * SXV + mx) * 8 + kc * 2)
+                                            : (uint32_t)(((mz * UW_PL + 2 * kc) * SUB_STRIDE) >> 4) + (uint32_t)(my * SXV + mx);
+                const uint32_t alo = (ib16 + aoff) | a_lbo;
+                const uint32_t blo = (w16 + (uint32_t)wslot * ((uint32_t)wstage >> 4) + (uint32_t)(a.swz ? k2 * 2 : k2 * (UW_KSTEP >> 4))) | b_lbo;
                 umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, (k2 == 0) ? acc : 1u);
               }
               umma_commit(&w_empty[wslot]);
             }
             __syncwarp();
             acc = 1u;
-            if (++wslot == UW_NW) { wslot = 0; wph ^= 1u; }
+            if (++wslot == nw) { wslot = 0; wph ^= 1u; }
           }
         }
         if (elect_one()) {
@@ -552,33 +572,46 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int rz = (warp - 2) >> 2;                // output z parity handled by this warp
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
-    const int qy = y0 + yl, qx = x0 + xl;
     constexpr int NCH = CP / 8;
-    // Epilogue operands (LeakyReLU' reference, accumulate target) are the long-latency part of a q-slice: the lines of the
-    // NEXT q-slice are pulled into L2 while this one is processed, and the registers of class block c4 + 1 are loaded
-    // before block c4 is converted, so the TMEM stage is released after ~one L2 latency instead of four DRAM latencies.
-    auto coords = [&](int zo, int c4, int& oz, int& oy, int& ox) -> bool {
-      oz = 2 * (z0 + zo) + rz - a.pad; oy = 2 * qy + (c4 >> 1) - a.pad; ox = 2 * qx + (c4 & 1) - a.pad;
-      return zo < nz && oz >= 0 && oz < a.L[0] && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2];
-    };
+    // The epilogue is instruction-latency bound (8 warps, a few hundred dependent instructions per class block), so all
+    // index arithmetic is hoisted: a thread owns ONE q-voxel, its four (ry,rx) classes are fixed element offsets from the
+    // (0,0) class, z advances by a constant stride, validity of a class is a per-thread constant.  The long-latency operands
+    // (LeakyReLU' reference, accumulate target) of the next q-slice are pulled into L2 while this one is processed and the
+    // registers of class block c4 + 1 are loaded before block c4 is converted.
+    const int oy0 = 2 * (y0 + yl) - a.pad, ox0 = 2 * (x0 + xl) - a.pad;
+    const int oz0 = 2 * z0 + rz - a.pad;
+    bool okc[4]; int ooff[4], roff[4];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int oy = oy0 + (c4 >> 1), ox = ox0 + (c4 & 1);
+      okc[c4] = !(a.dbg & 1) && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2] && co0 < a.Cout;
+      ooff[c4] = ((c4 >> 1) * a.OX + (c4 & 1)) * a.out_C;
+      roff[c4] = ((c4 >> 1) * a.RX + (c4 & 1)) * a.ref_C;
+    }
+    const int ncol = min(CP, a.Cout - co0);
+    const long long o_zs = 2LL * a.OY * a.OX * a.out_C, r_zs = 2LL * a.RY * a.RX * a.ref_C;      // two output slices per q-slice
+    bf16* const out0 = a.out + Epi::out_off(a, b, oz0, oy0, ox0) + co0;                        // class (0,0) voxel of q-slice 0
+    const bf16* const ref0 = a.ref ? a.ref + Epi::ref_off(a, b, oz0, oy0, ox0) + co0 : nullptr;
+    const uint32_t di0 = (uint32_t)(((((long long)b * a.L[0] + oz0) * a.L[1] + oy0) * a.L[2] + ox0) * a.Cout) + (uint32_t)co0;
+    const uint32_t di_zs = (uint32_t)(2 * a.L[1] * a.L[2] * a.Cout);
+    auto zok = [&](int zo) { const int oz = oz0 + 2 * zo; return zo < nz && oz >= 0 && oz < a.L[0]; };
     auto prefetch_l2 = [&](int zo) {
+      if (!zok(zo)) return;
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
-        int oz, oy, ox;
-        if (coords(zo, c4, oz, oy, ox) && co0 < a.Cout) {
-          if (a.ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0));
-          if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.out + Epi::out_off(a, b, oz, oy, ox) + co0));
+        if (okc[c4]) {
+          if (a.ref) asm volatile("prefetch.global.L2 [%0];" ::"l"(ref0 + zo * r_zs + roff[c4]));
+          if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(out0 + zo * o_zs + ooff[c4]));
         }
       }
     };
     auto fetch = [&](int zo, int c4, uint4* rq, uint4* aq) {
-      int oz, oy, ox;
-      if (coords(zo, c4, oz, oy, ox)) {
+      if (zok(zo) && okc[c4]) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          if (co0 + c * 8 < a.Cout) {
-            if (a.ref) rq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + co0 + c * 8));
-            if (a.accumulate) aq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + co0 + c * 8);
+          if (c * 8 < ncol) {
+            if (a.ref) rq[c] = __ldg(reinterpret_cast<const uint4*>(ref0 + zo * r_zs + roff[c4] + c * 8));
+            if (a.accumulate) aq[c] = *reinterpret_cast<const uint4*>(out0 + zo * o_zs + ooff[c4] + c * 8);
           }
         }
       }
@@ -588,6 +621,8 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     for (int zo = 0; zo < nz; ++zo) {
       prefetch_l2(zo + 1);
       fetch(zo, 0, refq[0], accq[0]);
+      const bool zv = zok(zo);
+      bf16* const outz = out0 + zo * o_zs;
       mbar_wait(&tfull_bar[zo & 1], ((uint32_t)(zo >> 1)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo & 1) * NP + (uint32_t)(rz * 4 * CP);
@@ -595,8 +630,6 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       for (int c4 = 0; c4 < 4; ++c4) {
         __syncwarp();
         if (c4 < 3) fetch(zo, c4 + 1, refq[(c4 + 1) & 1], accq[(c4 + 1) & 1]);
-        int oz, oy, ox;
-        const bool ok = coords(zo, c4, oz, oy, ox);
         uint32_t r[CP];
 #pragma unroll
         for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + (uint32_t)(c4 * CP + c), r + c);
@@ -605,14 +638,40 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tempty_bar[zo & 1]);
         }
-        if (ok) {
+        if (zv && okc[c4]) {
+          bf16* const op = outz + ooff[c4];
+          const uint32_t di = di0 + (uint32_t)zo * di_zs + (uint32_t)(((c4 >> 1) * a.L[2] + (c4 & 1)) * a.Cout);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            if (co0 + c * 8 < a.Cout) {
+            if (c * 8 < ncol) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              Epi::run(a, v, co0 + c * 8, b, oz, oy, ox, refq[c4 & 1][c], accq[c4 & 1][c]);
+              if (a.ref) {
+                const uint4 rq = refq[c4 & 1][c];
+                const uint32_t w[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {      // LeakyReLU'(ref): ref > 0 <=> sign bit clear and magnitude non-zero, on the raw bf16 halves
+                  if (!((w[i] & 0x7fffu) != 0u && (w[i] & 0x8000u) == 0u)) v[2 * i] *= a.ref_slope;
+                  if (!((w[i] & 0x7fff0000u) != 0u && (w[i] & 0x80000000u) == 0u)) v[2 * i + 1] *= a.ref_slope;
+                }
+              }
+              if (a.drop_key) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] *= 2.f * tem_keep(a.drop_key, di + (uint32_t)(c * 8 + u));
+              }
+              if (a.accumulate) {
+                float o[8]; unpack8(accq[c4 & 1][c], o);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] += o[u];
+              }
+              if (a.slope != 1.f) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * a.slope;
+              }
+              uint4 pk;
+              pk.x = pack2(v[0], v[1]); pk.y = pack2(v[2], v[3]); pk.z = pack2(v[4], v[5]); pk.w = pack2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(op + c * 8) = pk;
             }
           }
         }
@@ -628,20 +687,31 @@ conv_upw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 }
 
 // weight stages of the wide UP kernel: [cout group][chunk][tap = (mz,my,mx)][kc][k-half][n-group (32)][8][8], n = class*32 + co
-struct PackUpwArgs { const float* w; long long ws_tap, ws_in, ws_out; int nchunks, cout; bf16* dst; long long total; };
+// swizzled form: [cout group][chunk][tap][n (256 rows)][64 input channels], 16 B chunk index XOR (n & 7) (SWIZZLE_128B rows)
+struct PackUpwArgs { const float* w; long long ws_tap, ws_in, ws_out; int nchunks, cout, swz; bf16* dst; long long total; };
 __global__ void pack_weights_upw_kernel(const PackUpwArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
   long long t = i;
-  const int e = (int)(t & 7); t >>= 3;
-  const int r = (int)(t & 7); t >>= 3;
-  const int g = (int)(t & 31); t >>= 5;
-  const int j = (int)(t & 1); t >>= 1;
-  const int kc = (int)(t & 3); t >>= 2;
+  int e, n, kc, j;
+  if (a.swz) {
+    e = (int)(t & 7); t >>= 3;
+    const int ch = (int)(t & 7); t >>= 3;
+    n = (int)(t & 255); t >>= 8;
+    const int lc = ch ^ (n & 7);                         // logical 8-channel chunk stored at physical chunk ch
+    kc = lc >> 1; j = lc & 1;
+  } else {
+    e = (int)(t & 7); t >>= 3;
+    const int r = (int)(t & 7); t >>= 3;
+    const int g = (int)(t & 31); t >>= 5;
+    j = (int)(t & 1); t >>= 1;
+    kc = (int)(t & 3); t >>= 2;
+    n = g * 8 + r;
+  }
   const int tap = (int)(t & 7); t >>= 3;
   const int c = (int)(t % a.nchunks); t /= a.nchunks;
   const int cg = (int)t;
-  const int n = g * 8 + r, cls = n >> 5, co = cg * 32 + (n & 31);
+  const int cls = n >> 5, co = cg * 32 + (n & 31);
   const int rz = cls >> 2, ry = (cls >> 1) & 1, rx = cls & 1;
   const int mz = tap >> 2, my = (tap >> 1) & 1, mx = tap & 1;
   const int kz = rz + 2 * (1 - mz), ky = ry + 2 * (1 - my), kx = rx + 2 * (1 - mx);
@@ -871,6 +941,10 @@ __global__ void pack_weights_dw_kernel(const PackDwArgs a) {
   a.dst[i] = __float2bfloat16_rn(v);
 }
 
+int wide_swizzle() {       // debug knob: 8-channel plane tiles (SWIZZLE_NONE) in the wide UP kernel
+  static const int v = getenv("TEM_S2_NO_SWIZZLE") ? 0 : 1;
+  return v;
+}
 int dw_np(int cout) { const int n = (cout + 63) / 64 * 64; return n > 256 ? 256 : n; }
 
 // bf16 UMMA B image [step][k-half][n-group][8 rows][8 elems]; the step order is the issue order of the kernels above
@@ -978,7 +1052,7 @@ cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
   const int v = variant_of(a);
   if (v == 1) {
     PackUpwArgs q; q.w = a.w; q.ws_tap = a.ws_tap; q.ws_in = a.ws_in; q.ws_out = a.ws_out;
-    q.nchunks = a.C0 / 64; q.cout = a.Cout; q.dst = dst; q.total = (long long)(tc_s2_packed_bytes(a) / 2);
+    q.nchunks = a.C0 / 64; q.cout = a.Cout; q.swz = wide_swizzle(); q.dst = dst; q.total = (long long)(tc_s2_packed_bytes(a) / 2);
     pack_weights_upw_kernel<<<(unsigned)((q.total + 255) / 256), 256, 0, st>>>(q); ++g_tem_launches;
     return cudaGetLastError();
   }
@@ -1007,6 +1081,20 @@ static bool make_map_s2(CUtensorMap* m, const void* base, int B, int Z, int Y, i
   cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// [voxel][64 channels] tiles of 17 x 9 voxels in the 128B-swizzle layout (es = 2: every second voxel / row, the parity split)
+static bool make_map_sw128(CUtensorMap* m, const void* base, int B, int Z, int Y, int X, int C, int es) {
+  EncodeTiledFn enc = tem_get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)Z, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)X * C * 2, (cuuint64_t)Y * X * C * 2, (cuuint64_t)Z * Y * X * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)(SXV * es), (cuuint32_t)(SYR * es), 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -1043,11 +1131,14 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   CUtensorMap m0;
+  t.swz = wide_swizzle();
+  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
   if (variant == 1) {
-    if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue;
+    if (t.swz) { if (!make_map_sw128(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 1)) return cudaErrorInvalidValue; }
+    else if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue;
     const int groups = (a.Cout + 31) / 32;
     pick_chunks(cols * groups, t.Q[0], 1 << 20, 1, t.zc, t.nzc);
-    const size_t smem = (size_t)UW_NIN * UW_IN_STAGE + (size_t)UW_NW * UW_WSTAGE + 1024;
+    const size_t smem = (size_t)UW_NIN * UW_IN_STAGE + (size_t)UW_WRING + 1024;
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv_upw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }
     conv_upw_tc_kernel<<<dim3((unsigned)(cols * t.nzc), (unsigned)groups), kThreadsUpw, smem, st>>>(m0, t);

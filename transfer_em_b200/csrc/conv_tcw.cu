@@ -46,6 +46,7 @@ struct TcwArgs {
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
   uint32_t drop_key;
   int accumulate;
+  int dbg;                     // experiment bits (TEM_S2_DBG): 1 no epilogue memory traffic, 2 no weight loads, 4 no input loads
 };
 
 __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
@@ -93,18 +94,24 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       for (int c = 0; c < a.nchunks; ++c) {
         const int wb = c & 1;
         mbar_wait(&wempty_bar[wb], (((uint32_t)(c >> 1)) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&wfull_bar[wb], (uint32_t)WBYTES);
-        bulk_load(wsm + wb * WBYTES, reinterpret_cast<const uint8_t*>(a.wpacked) + ((size_t)cg * a.nchunks + c) * WBYTES, (uint32_t)WBYTES, &wfull_bar[wb]);
+        if (a.dbg & 2) mbar_arrive(&wfull_bar[wb]);
+        else {
+          mbar_arrive_expect_tx(&wfull_bar[wb], (uint32_t)WBYTES);
+          bulk_load(wsm + wb * WBYTES, reinterpret_cast<const uint8_t*>(a.wpacked) + ((size_t)cg * a.nchunks + c) * WBYTES, (uint32_t)WBYTES, &wfull_bar[wb]);
+        }
         const bool src1 = c >= a.chunks0;
         const CUtensorMap* mp = src1 ? &map1 : &map0;
         const int pl0 = (src1 ? c - a.chunks0 : c) * WPL;
         const int sx = x0 + (src1 ? a.shift1[2] : a.shift0[2]), sy = y0 + (src1 ? a.shift1[1] : a.shift0[1]), sz = z0 + (src1 ? a.shift1[0] : a.shift0[0]);
         for (int s = 0; s < nslices; ++s) {
           mbar_wait(&empty_bar[slot], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WPL * PLANE_BYTES);
-          uint8_t* dst = ring + (size_t)slot * SLOT_BYTES;
+          if (a.dbg & 4) mbar_arrive(&full_bar[slot]);
+          else {
+            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WPL * PLANE_BYTES);
+            uint8_t* dst = ring + (size_t)slot * SLOT_BYTES;
 #pragma unroll
-          for (int p = 0; p < WPL; ++p) tma_load_5d(dst + p * PLANE_STRIDE, mp, &full_bar[slot], (pl0 + p) * 8, sx, sy, sz + s, b);
+            for (int p = 0; p < WPL; ++p) tma_load_5d(dst + p * PLANE_STRIDE, mp, &full_bar[slot], (pl0 + p) * 8, sx, sy, sz + s, b);
+          }
           if (++slot == RINGW) { slot = 0; ph ^= 1u; }
         }
       }
@@ -154,7 +161,7 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
     const int oy = y0 + yl, ox = x0 + xl;
-    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int c = 0; c < 512; c += 8) tmem_st8_zero(lane_base + (uint32_t)c);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -304,6 +311,7 @@ cudaError_t launch_conv_tcw(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.Cout = a.Cout; t.slope = a.slope;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
   CUtensorMap m0, m1;
   if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
   if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }

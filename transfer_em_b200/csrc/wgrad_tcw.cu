@@ -37,6 +37,7 @@ struct WwArgs {
   int nrg, ncb, nzc, zc, units;
   int xa_bytes, gb_bytes;
   float* dw; long long ws_tap, ws_a, ws_b;
+  int dbg;                     // experiment bits (TEM_S2_DBG): 1 no epilogue atomics, 4 no x loads, 8 no g loads
 };
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t lo, uint32_t hi) {
@@ -98,10 +99,14 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
         mbar_wait(&gempty[gslot], gph ^ 1u);
         mbar_wait(&xempty[xslot], xph ^ 1u);
         if (elect_one()) {
+          if (a.dbg & 8) mbar_arrive(&gfull[gslot]);
+          else {
           mbar_arrive_expect_tx(&gfull[gslot], (uint32_t)a.gb_bytes);
           uint8_t* gd = gring + (size_t)gslot * a.gb_bytes;
 #pragma unroll
           for (int p = 0; p < NBW / 8; ++p) tma_load_5d(gd + p * gplane, &mapg, &gfull[gslot], (cbb * (NBW / 8) + p) * 8, x0, y0, z0 + s, b);
+          }
+          if (a.dbg & 4) { mbar_arrive(&xfull[xslot]); } else {
           mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
           uint8_t* xd = xring + (size_t)xslot * a.xa_bytes;
           const int cx = a.s2 ? 2 * (x0 + mlo(rx)) + rx + a.shift[2] : x0 + a.shift[2];
@@ -109,6 +114,7 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
           const int cz = a.s2 ? 2 * (z0 + s + mlo(rz) + mz) + rz + a.shift[0] : z0 + s + dz + a.shift[0];
           for (int p = 0; p < pa; ++p)
             tma_load_5d(xd + p * xplane, &mapx, &xfull[xslot], (cab * pa + p) * 8, cx, cy, cz, b);
+          }
         }
         __syncwarp();
         if (++gslot == GRW) { gslot = 0; gph ^= 1u; }
@@ -181,7 +187,7 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
         uint32_t r[8];
         tmem_ld8(lane_base + (uint32_t)(t * NBW + c), r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (rowok && any) {
+        if (rowok && any && !(a.dbg & 1)) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float v = __uint_as_float(r[e]);
@@ -224,6 +230,7 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
   const int ra = t.s2 ? RB + 1 : RA;
   t.xa_bytes = (t.M / 8) * ra * WA * 16; t.gb_bytes = (NBW / 8) * RB * WB * 16;
   t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
+  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
   t.nrg = (w.L[1] + RB - 1) / RB; t.ncb = (w.L[2] + WB - 1) / WB;
   const int gy = (t.s2 ? 16 : 3) * t.n_ca * t.n_cb;
   int gx = 148 / gy; if (gx < 1) gx = 1;
