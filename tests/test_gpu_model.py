@@ -99,10 +99,9 @@ def test_api_errors_match_reference():
     assert shapes[0] == (3, 3, 3, 1, 8) and shapes[6] == (4, 4, 4, 16, 32) and shapes[11] == (3, 3, 3, 16, 1)
 
 
-def _train_case(is3d, B, dropout, seed, loss_mode='focal', scale=2.0):
+def _train_case(is3d, B, dropout, seed, loss_mode='focal', scale=2.0, wf=8):
     # weights at 2x the init scale: activations O(0.1-1) but D logits not saturated (at 4x the focal-loss derivative
     # (1-p)^2 amplifies a 1e-3 logit difference into a 10 % change of the whole adversarial gradient, for any implementation)
-    wf = 8
     P = _params(wf, is3d, seed, scale)
     P['dx'][9] = np.array([0.1], np.float32); P['dy'][9] = np.array([-0.2], np.float32)
     model = EM2EM(74, "parity", is3d=is3d, wf=wf, max_batch=B, dropout=dropout, loss_mode=loss_mode,
@@ -124,7 +123,7 @@ def _cos(a, b):
     return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
 
 
-def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol=3 * TOL):
+def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol=3 * TOL, wf=8, grad_tol=TOL):
     """Forward outputs and losses are compared with the plain fp32 oracle (north-star tolerance 1e-2; the loss
     vector gets 2e-2 because the adversarial terms hang off a single logit per sample that sits behind
     21 bf16-stored layers -- against the oracle at stored values they agree to 2e-3).
@@ -137,7 +136,7 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
     however exact its kernels (measured: 3-9e-2 against the fp32 oracle, <= 6e-3 at identical stored values).
     Against the fp32 oracle the gradient's direction and norm are bounded instead."""
     losses = model.engine.train_grads(rx, ry)
-    ref = O.train_step_grads(P, rx, ry, 8, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode, keep_outputs=True)
+    ref = O.train_step_grads(P, rx, ry, wf, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode, keep_outputs=True)
     b = (rx.shape[1] - ref.outputs["same_x"].shape[1]) // 2
     crop = (slice(None),) + (slice(b, -b),) * (rx.ndim - 2) + (slice(None),)
     assert max(np.abs(rx[crop] - ref.outputs["same_x"]).max(), np.abs(ry[crop] - ref.outputs["same_y"]).max()) < 1.9
@@ -147,7 +146,7 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
         assert rel_l2(model.engine.train_output(name), ref.outputs[name]) < 3 * TOL, name
     np.testing.assert_allclose(np.array(losses), np.array(ref.losses), rtol=loss_rtol, atol=1e-4)
     ov = {'fake_y': model.engine.train_output('fake_y'), 'fake_x': model.engine.train_output('fake_x')}
-    refq = O.train_step_grads(P, rx, ry, 8, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode,
+    refq = O.train_step_grads(P, rx, ry, wf, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode,
                               quant=O.bf16_round, qweights=True, override_fakes=ov, keep_outputs=True)
     for name in ("fake_y", "cycled_x", "fake_x", "cycled_y", "same_x", "same_y"):
         assert rel_l2(model.engine.train_output(name), refq.outputs[name]) < 8e-3, name
@@ -159,7 +158,7 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
         flat_q = np.concatenate([g.reshape(-1) for g in refq.grads[k]])
         flat_r = np.concatenate([g.reshape(-1) for g in ref.grads[k]])
         worst[k] = rel_l2(flat_g, flat_q)
-        assert worst[k] < TOL, f"gradient of net {k}: rel-L2 {worst[k]} vs oracle at stored values"
+        assert worst[k] < grad_tol, f"gradient of net {k}: rel-L2 {worst[k]} vs oracle at stored values"
         assert _cos(flat_g, flat_r) > 0.995 and abs(np.linalg.norm(flat_g) / np.linalg.norm(flat_r) - 1) < 2e-2, k
         for (vname, _, _), a, b in zip(model.engine.variables(net), got, refq.grads[k]):
             if np.linalg.norm(b) > 0:
@@ -175,6 +174,16 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
 def test_train_step_gradients_no_dropout(is3d, B):
     model, P, rx, ry = _train_case(is3d, B, False, 21)
     _check_step(model, P, rx, ry, is3d)
+
+
+def test_train_step_gradients_wide_model():
+    """wf = 4 (16 / 32 / 64 channels; d4 64 -> 64, g6 64 -> 32): the train step on the wide-layer kernels -- conv_upw_tc /
+    conv_downw_tc (streamed weights, swizzled tiles), conv3_tcw, wgrad_tcw in both forms -- against the same oracle."""
+    model, P, rx, ry = _train_case(True, 1, False, 27, scale=1.5, wf=4)
+    # per-network gradient band 2e-2 here: measured g / f / d_x < 1e-2, d_y 1.4e-2 (one logit per sample behind 64-channel
+    # layers whose K = 4096 sums sit closer to the bf16 rounding boundaries of the stored activations; see _check_step)
+    _, _, worst = _check_step(model, P, rx, ry, True, wf=4, grad_tol=2 * TOL)
+    print("wide-model gradient rel-L2 per network:", worst)
 
 
 def test_train_step_gradients_with_injected_dropout_masks():

@@ -46,6 +46,7 @@ struct TcwArgs {
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
   uint32_t drop_key;
   int accumulate;
+  int swz;                     // input tiles as [voxel][32 ch] rows in the 64B-swizzle layout (one TMA request per voxel)
   int dbg;                     // experiment bits (TEM_S2_DBG): 1 no epilogue memory traffic, 2 no weight loads, 4 no input loads
 };
 
@@ -109,8 +110,11 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           else {
             mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WPL * PLANE_BYTES);
             uint8_t* dst = ring + (size_t)slot * SLOT_BYTES;
+            if (a.swz) tma_load_5d(dst, mp, &full_bar[slot], pl0 * 8, sx, sy, sz + s, b);
+            else {
 #pragma unroll
-            for (int p = 0; p < WPL; ++p) tma_load_5d(dst + p * PLANE_STRIDE, mp, &full_bar[slot], (pl0 + p) * 8, sx, sy, sz + s, b);
+              for (int p = 0; p < WPL; ++p) tma_load_5d(dst + p * PLANE_STRIDE, mp, &full_bar[slot], (pl0 + p) * 8, sx, sy, sz + s, b);
+            }
           }
           if (++slot == RINGW) { slot = 0; ph ^= 1u; }
         }
@@ -122,10 +126,12 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t wb16 = smem_u32(wsm) >> 4;
     const uint32_t rbase = smem_u32(ring);
-    const uint32_t a_hi = ((uint32_t)(HX * 16) >> 4) | (1u << 14);          // SBO = one halo row
+    // A operand: 8-channel planes (SBO = one halo row, LBO = next plane), or rows of 32 channels (64 B, SWIZZLE_64B as TMA
+    // writes them; SBO = one halo row of 10 voxels, K-step = 32 B further in the row, tap = start shifted by whole rows)
+    const uint32_t a_hi = a.swz ? (((uint32_t)(HX * 64) >> 4) | (1u << 14) | (4u << 29)) : (((uint32_t)(HX * 16) >> 4) | (1u << 14));
     const uint32_t b_hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B between n-groups
     const uint32_t b_lbo = ((uint32_t)(NPW * 16) >> 4) << 16;
-    const uint32_t a_lbo = ((uint32_t)PLANE_STRIDE >> 4) << 16;             // K halves = two consecutive planes
+    const uint32_t a_lbo = a.swz ? (1u << 16) : (((uint32_t)PLANE_STRIDE >> 4) << 16);   // K halves = two consecutive planes
     int slot = 0; uint32_t ph = 0;
     for (int c = 0; c < a.nchunks; ++c) {
       const int wb = c & 1;
@@ -140,11 +146,11 @@ conv3_tcw_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           uint32_t blo = (wb16 + (uint32_t)(wb * WBYTES >> 4)) | b_lbo;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            uint32_t alo = (sb16 + (uint32_t)((t / 3) * HX + (t % 3))) | a_lbo;
+            uint32_t alo = (sb16 + (uint32_t)((t / 3) * HX + (t % 3)) * (a.swz ? 4u : 1u)) | a_lbo;
 #pragma unroll
             for (int kc = 0; kc < WCH / 16; ++kc) {
               umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
-              alo += (uint32_t)(2 * PLANE_STRIDE) >> 4;
+              alo += a.swz ? 2u : ((uint32_t)(2 * PLANE_STRIDE) >> 4);
               blo += (uint32_t)(NPW * 32) >> 4;
             }
           }
@@ -299,6 +305,20 @@ cudaError_t tcw_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// [voxel][32 channels] halo tiles (64 B rows) in the 64B-swizzle layout
+static bool make_map_sw64(CUtensorMap* m, const void* base, int B, int Z, int Y, int X, int C) {
+  EncodeTiledFn enc = tem_get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)Z, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)X * C * 2, (cuuint64_t)Y * X * C * 2, (cuuint64_t)Z * Y * X * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)WCH, (cuuint32_t)HX, (cuuint32_t)HY, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 cudaError_t launch_conv_tcw(const ConvArgs& a, const bf16* wpacked, cudaStream_t st) {
   TcwArgs t; memset(&t, 0, sizeof(t));
   t.B = a.B; for (int i = 0; i < 3; ++i) t.L[i] = a.L[i];
@@ -312,10 +332,18 @@ cudaError_t launch_conv_tcw(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
+  static const int swz = getenv("TEM_TCW_NO_SWIZZLE") ? 0 : 1;             // debug knob: 8-channel plane tiles
+  t.swz = swz;
   CUtensorMap m0, m1;
-  if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
-  if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
-  else m1 = m0;
+  if (swz) {
+    if (!make_map_sw64(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C)) return cudaErrorInvalidValue;
+    if (a.C1) { if (!make_map_sw64(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C)) return cudaErrorInvalidValue; }
+    else m1 = m0;
+  } else {
+    if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
+    if (a.C1) { if (!tem_make_map_5d(&m1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
+    else m1 = m0;
+  }
   const size_t smem = (size_t)2 * WBYTES + (size_t)RINGW * SLOT_BYTES + 1024;
   static bool attr = false;
   if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv3_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }

@@ -992,7 +992,13 @@ extern "C" int tem_train_step(tem_handle* h, const void* real_x, const void* rea
   float scale = 1.f;
   if (h->comm && h->world > 1) {
     // per-replica losses are means over the local batch: the global-batch mean is the rank average (cgan.py:8-11)
-    TEM_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->arena_elems, kNcclFloat32, kNcclSum, h->comm, st));
+    // flat gradient arena [G | F | D_x | D_y | loss slots] in buckets of <= 25 MB (TEM_BUCKET_MB): one bucket at wf = 8
+    // (2.49 MB), five at wf = 1 (112.9 MB); all on the compute stream, NCCL pipelines consecutive buckets over NVLink
+    static const long long bucket_elems = []() { const char* e = getenv("TEM_BUCKET_MB"); const long long mb = e ? atoll(e) : 25; return (mb > 0 ? mb : 25) * (1LL << 20) / 4; }();
+    for (long long off = 0; off < (long long)h->arena_elems; off += bucket_elems) {
+      const long long n = std::min<long long>(bucket_elems, (long long)h->arena_elems - off);
+      TEM_NCCL(g_nccl.AllReduce(h->grads + off, h->grads + off, (size_t)n, kNcclFloat32, kNcclSum, h->comm, st));
+    }
     scale = 1.f / (float)h->world;
   }
   TEM_CHECK(write_losses(h, scale, losses_out, st));
