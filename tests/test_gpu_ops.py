@@ -372,6 +372,7 @@ WIDE_S2_CASES = [
     (4, 2, 64, 32, True, (4, 18, 9)),        # g6 at wf = 4: fwd = wide UP (one cout group), dgrad = wide DOWN (Cin 32)
     (4, 2, 64, 256, False, (20, 6, 8)),      # NP = 256: two output slices per TMEM strip, several z chunks
     (4, 2, 64, 40, False, (6, 8, 8)),        # Cout not a multiple of the column groups
+    (4, 2, 32, 32, False, (20, 36, 38)),     # g2 at wf = 2: too many weights for the resident kernel, half of the NP = 64 columns used
 ]
 
 
@@ -394,7 +395,7 @@ def test_wide_stride2_tcgen05_fwd_dgrad(k, s, cin, cout, tr, dims):
     dy = bf16r(r.standard_normal(ref.shape))
     act = bf16r(r.standard_normal(x.shape))
     dx = conv_dgrad(_cuda(dy, torch.bfloat16), wg, d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
-    if tr or cout % 64 == 0:      # the data gradient reads `cout` channels: wide UP needs 64-channel chunks
+    if tr or cout % 64 == 0:      # the data gradient reads `cout` channels: wide UP needs 64-channel chunks (else resident kernel)
         assert lib.tem_last_kernel().decode() == ("conv_downw_tc_kernel" if tr else "conv_upw_tc_kernel")
     dref = (naive.convT_dgrad(dy, w, x.shape) if tr else naive.conv_dgrad(dy, w, s, x.shape)) * naive.lrelu_grad_from_output(act, 0.3)
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 4)

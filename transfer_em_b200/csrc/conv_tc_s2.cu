@@ -1017,7 +1017,9 @@ int variant_of(const ConvArgs& a) {
     if (smem <= 200 * 1024) return 0;
   }
   if (a.form == 1 && cin >= 64 && cin % 64 == 0) return 1;
-  if (a.form == 0 && cin >= 16 && cin % 16 == 0 && (a.Cout > 32 || cin > 64)) return 2;   // 32 -> 32 stays on conv_mma.cu
+  // 32 -> 32 (weights do not fit beside the ring of the resident kernel): wide kernel unless the layer is tiny (d4 at wf = 8)
+  const long long vox = (long long)a.B * a.L[0] * a.L[1] * a.L[2];
+  if (a.form == 0 && cin >= 16 && cin % 16 == 0 && (a.Cout > 32 || cin > 64 || vox >= 4096)) return 2;
   return -1;
 }
 
