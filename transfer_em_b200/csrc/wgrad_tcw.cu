@@ -37,6 +37,7 @@ struct WwArgs {
   int nrg, ncb, nzc, zc, units;
   int xa_bytes, gb_bytes;
   float* dw; long long ws_tap, ws_a, ws_b;
+  int swz;                     // tiles as [voxel][64 | 32 ch] rows in the 128B / 64B swizzle layouts (one TMA request per voxel)
   int dbg;                     // experiment bits (TEM_S2_DBG): 1 no epilogue atomics, 4 no x loads, 8 no g loads
 };
 
@@ -103,8 +104,11 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
           else {
           mbar_arrive_expect_tx(&gfull[gslot], (uint32_t)a.gb_bytes);
           uint8_t* gd = gring + (size_t)gslot * a.gb_bytes;
+          if (a.swz) tma_load_5d(gd, &mapg, &gfull[gslot], cbb * NBW, x0, y0, z0 + s, b);
+          else {
 #pragma unroll
-          for (int p = 0; p < NBW / 8; ++p) tma_load_5d(gd + p * gplane, &mapg, &gfull[gslot], (cbb * (NBW / 8) + p) * 8, x0, y0, z0 + s, b);
+            for (int p = 0; p < NBW / 8; ++p) tma_load_5d(gd + p * gplane, &mapg, &gfull[gslot], (cbb * (NBW / 8) + p) * 8, x0, y0, z0 + s, b);
+          }
           }
           if (a.dbg & 4) { mbar_arrive(&xfull[xslot]); } else {
           mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
@@ -112,6 +116,10 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
           const int cx = a.s2 ? 2 * (x0 + mlo(rx)) + rx + a.shift[2] : x0 + a.shift[2];
           const int cy = a.s2 ? 2 * (y0 + mlo(ry)) + ry + a.shift[1] : y0 + a.shift[1];
           const int cz = a.s2 ? 2 * (z0 + s + mlo(rz) + mz) + rz + a.shift[0] : z0 + s + dz + a.shift[0];
+          if (a.swz) {
+            for (int c = 0; c < (a.M >> 6); ++c)
+              tma_load_5d(xd + c * (xplane * 8), &mapx, &xfull[xslot], (cab * (a.M >> 6) + c) * 64, cx, cy, cz, b);
+          } else
           for (int p = 0; p < pa; ++p)
             tma_load_5d(xd + p * xplane, &mapx, &xfull[xslot], (cab * pa + p) * 8, cx, cy, cz, b);
           }
@@ -123,8 +131,13 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
     }
   } else if (warp == 1) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NBW >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+    // plane layout (MN-major INTERLEAVE): LBO = 128 B (next 8 voxels along K), SBO = plane stride (next 8 channels along M / N).
+    // swizzled rows (MN-major SW128 for x, SW64 for g): a row = one voxel (64 / 32 channels), SBO = 8 rows (next 8 voxels
+    // along K), LBO = next 64-channel chunk of x (M = 128); a tap is still a start address shifted by whole rows.
     const uint32_t lo_fixed = (128u >> 4) << 16;                                   // LBO = 128 B (next 8 voxels)
-    const uint32_t a_hi = ((uint32_t)xplane >> 4) | (1u << 14), b_hi = ((uint32_t)gplane >> 4) | (1u << 14);   // SBO = plane stride
+    const uint32_t a_lo_sw = (((uint32_t)xplane * 8u) >> 4) << 16;                 // LBO = one 64-channel chunk of the x tile
+    const uint32_t a_hi = a.swz ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : (((uint32_t)xplane >> 4) | (1u << 14));
+    const uint32_t b_hi = a.swz ? ((512u >> 4) | (1u << 14) | (4u << 29)) : (((uint32_t)gplane >> 4) | (1u << 14));   // SBO = plane stride
     const uint32_t xbase16 = smem_u32(xring) >> 4, gbase16 = smem_u32(gring) >> 4;
     const uint32_t xa16 = (uint32_t)a.xa_bytes >> 4, gb16 = (uint32_t)a.gb_bytes >> 4;
     int xslot = 0; uint32_t xph = 0; int gslot = 0; uint32_t gph = 0;
@@ -135,19 +148,20 @@ wgrad_tcw_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant
         mbar_wait(&gfull[gslot], gph);
         mbar_wait(&xfull[xslot], xph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t xs = (xbase16 + (uint32_t)xslot * xa16) | lo_fixed;
+        const uint32_t xs = a.swz ? ((xbase16 + (uint32_t)xslot * xa16) | a_lo_sw) : ((xbase16 + (uint32_t)xslot * xa16) | lo_fixed);
         const uint32_t gs = (gbase16 + (uint32_t)gslot * gb16) | lo_fixed;
+        const uint32_t xm = a.swz ? 8u : 1u, gm = a.swz ? 4u : 1u;                 // 16 B units per voxel row
         if (elect_one()) {
 #pragma unroll 1
           for (int j = 0; j < RB; ++j) {
 #pragma unroll
             for (int r = 0; r < XB; ++r) {
-              const uint64_t bd = desc_mn(gs + (uint32_t)(j * WB + 16 * r), b_hi);
+              const uint64_t bd = desc_mn(gs + (uint32_t)(j * WB + 16 * r) * gm, b_hi);
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
                 if (t < ntap) {
                   const int ty = a.s2 ? (t >> 1) : t / 3, tx = a.s2 ? (t & 1) : t % 3;
-                  const uint64_t ad = desc_mn(xs + (uint32_t)((j + ty) * WA + 16 * r + tx), a_hi);
+                  const uint64_t ad = desc_mn(xs + (uint32_t)((j + ty) * WA + 16 * r + tx) * xm, a_hi);
                   umma_bf16(tmem_base + (uint32_t)(t * NBW), ad, bd, idesc, acc);
                 }
               }
@@ -241,19 +255,26 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
   t.zc = (w.L[0] + nzc - 1) / nzc; t.nzc = (w.L[0] + t.zc - 1) / t.zc;
   t.units = (int)(cols * t.nzc);
   if (gx > t.units) gx = t.units;
+  static const int swz = getenv("TEM_WGRAD_TCW_NO_SWIZZLE") ? 0 : 1;     // debug knob: 8-channel plane tiles
+  t.swz = swz;
   CUtensorMap mx, mg;
-  if (!t.s2) { if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, WA, RA)) return cudaErrorInvalidValue; }
-  else {      // de-interleaved tiles: every second voxel of every second row (element strides), as in conv_tc_s2.cu
+  {     // x: (de-interleaved in the stride-2 form: every second voxel of every second row through TMA element strides, as in conv_tc_s2.cu)
     EncodeTiledFn enc = tem_get_encode();
     if (!enc) return cudaErrorInvalidValue;
+    const int es = t.s2 ? 2 : 1;
     cuuint64_t dims[5] = {(cuuint64_t)w.S.C, (cuuint64_t)w.S.X, (cuuint64_t)w.S.Y, (cuuint64_t)w.S.Z, (cuuint64_t)w.B};
     cuuint64_t strides[4] = {(cuuint64_t)w.S.C * 2, (cuuint64_t)w.S.X * w.S.C * 2, (cuuint64_t)w.S.Y * w.S.X * w.S.C * 2, (cuuint64_t)w.S.Z * w.S.Y * w.S.X * w.S.C * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)(WA * 2), (cuuint32_t)(ra * 2), 1, 1};
-    cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(swz ? 64 : 8), (cuuint32_t)(WA * es), (cuuint32_t)(ra * es), 1, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
     if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(w.S.p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+            swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    cuuint64_t gdims[5] = {(cuuint64_t)w.p_C, (cuuint64_t)w.PX, (cuuint64_t)w.PY, (cuuint64_t)w.PZ, (cuuint64_t)w.B};
+    cuuint64_t gstr[4] = {(cuuint64_t)w.p_C * 2, (cuuint64_t)w.PX * w.p_C * 2, (cuuint64_t)w.PY * w.PX * w.p_C * 2, (cuuint64_t)w.PZ * w.PY * w.PX * w.p_C * 2};
+    cuuint32_t gbox[5] = {(cuuint32_t)(swz ? NBW : 8), (cuuint32_t)WB, (cuuint32_t)RB, 1, 1};
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    if (enc(&mg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(w.P), gdims, gstr, gbox, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swz ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
-  if (!tem_make_map_5d(&mg, w.P, w.B, w.PZ, w.PY, w.PX, w.p_C, WB, RB)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)XRW * t.xa_bytes + (size_t)GRW * t.gb_bytes + 1024;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   static bool attr = false;
