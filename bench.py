@@ -288,7 +288,12 @@ def main():
             c = max(caps, key=lambda c: rep[c["tag"]]["bytes"])
             traffic = c["dram_bytes_per_launch"]
             traffic_of = {"layer": c["tag"], "algorithmic_bytes": rep[c["tag"]]["bytes"], "capture": "profiles/ncu_r1_" + c["capture"] + ".txt"}
-    roofline = {"kernel": tname, "bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
+    # which roofline bounds the dominant kernel: its arithmetic intensity against the ridge of the measured peaks (the wf = 8
+    # layers of config 3 sit below it: HBM; the 64-256 channel layers of config 4 far above: bf16 tensor cores)
+    tensor_bound = t["flops"] / max(t["bytes"], 1.0) > (tf_sus * 1e12) / (hbm * 1e9)
+    roofline = {"kernel": tname, "bound": "tensor" if tensor_bound else "hbm", "achieved": ach_tf if tensor_bound else ach_gbs,
+                "peak": tf_sus if tensor_bound else hbm, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": (ach_tf / tf_sus) if tensor_bound else (ach_gbs / hbm), "achieved_gbs": ach_gbs,
                 "traffic": traffic, "traffic_of": traffic_of, "peak_source": pk_src, "avg_launch_ms": per_launch_ms, "launches_per_step": t["count"] / PK,
                 "share_of_conv_time": t["ms"] / tot_ms, "achieved_tflops": ach_tf,
                 "algorithmic_bytes_per_launch": t["bytes"] / t["count"], "flops_per_launch": t["flops"] / t["count"],

@@ -274,6 +274,12 @@ WG_CASES = [
     (4, 2, 128, 64, False, (8, 10, 12)),
     (4, 2, 64, 64, True, (5, 7, 9)),
     (4, 2, 32, 128, True, (6, 5, 18)),
+    # N = 64 / 128 output channels per CTA: (dz, dy) split in the stride-1 form, two 64-channel swizzled chunks per g tile
+    (3, 1, 128, 128, False, (6, 9, 37)),
+    (3, 1, 64, 256, False, (5, 7, 20)),
+    (3, 1, 256, 64, False, (7, 6, 11)),
+    (4, 2, 128, 128, False, (8, 10, 38)),
+    (4, 2, 256, 128, True, (4, 5, 9)),
 ]
 
 
