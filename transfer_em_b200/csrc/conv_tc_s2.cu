@@ -776,6 +776,8 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       for (int j = 0; j <= nz; ++j) {
         mbar_wait(&in_empty[slot], ph ^ 1u);
         if (elect_one()) {
+          if (a.dbg & 4) mbar_arrive(&in_full[slot]);
+          else {
           mbar_arrive_expect_tx(&in_full[slot], 16u * SUB_BYTES);
           uint8_t* dst = inring + (size_t)slot * DW_STAGE;
           for (int sl = 0; sl < 2; ++sl) {
@@ -787,6 +789,7 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
               for (int p = 0; p < 2; ++p)
                 tma_load_5d(dst + ((sl * 4 + rr) * 2 + p) * SUB_STRIDE, &map0, &in_full[slot], (2 * c + p) * 8, cx, cy, zin, b);
             }
+          }
           }
         }
         __syncwarp();
@@ -804,8 +807,11 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           for (int i = 0; i < nst; ++i) {
             mbar_wait(&w_empty[slot], ph ^ 1u);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&w_full[slot], (uint32_t)wstage);
-              bulk_load(wring + (size_t)slot * DW_WSLOT, src + (size_t)i * wstage, (uint32_t)wstage, &w_full[slot]);
+              if (a.dbg & 2) mbar_arrive(&w_full[slot]);
+              else {
+                mbar_arrive_expect_tx(&w_full[slot], (uint32_t)wstage);
+                bulk_load(wring + (size_t)slot * DW_WSLOT, src + (size_t)i * wstage, (uint32_t)wstage, &w_full[slot]);
+              }
             }
             __syncwarp();
             if (++slot == DW_WMAX) { slot = 0; ph ^= 1u; }
@@ -863,7 +869,7 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
     const int oy = y0 + yl, ox = x0 + xl;
-    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
     const int cbeg = half * (NP >> 1), cend = cbeg + (NP >> 1);
     if (inside && (a.ref || a.accumulate)) {            // epilogue operands of the whole strip into L2 while the MMAs run
       for (int zo = 0; zo < nz; ++zo)
