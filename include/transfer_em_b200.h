@@ -162,6 +162,12 @@ int tem_augment(const void* in, int in_dtype, const float meanstd[2], float* out
 /* datasets.py:173-190 get_meanstd(), one tensor: out[0] = tf.math.reduce_mean, out[1] = tf.math.reduce_variance (population).
    scratch: 32 zeroed bytes of device memory, left zeroed. */
 int tem_mean_var(const float* in, int64_t n, void* scratch, float* out, void* stream);
+/* debug.py:7-63 warp_tensor() on one [Z,Y,X] (2-D: Z = 1, ndims = 2) fp32 tensor: box blur 3^ndims ('SAME', zero padding,
+   filter 1/27 or 1/9), then every voxel whose 4^ndims 'SAME' window (offsets -1..+2) holds a seed uniform[v] < hole_rate
+   (the reference draws tf.random.uniform; here the caller passes the draw) is set to the mean of the blurred tensor.
+   scratch: 8 bytes of device memory.  in and out must not alias. */
+int tem_warp_tensor(const float* in, const float* uniform, float* out, const int32_t dims_zyx[3], int32_t ndims,
+                    float hole_rate, void* scratch, void* stream);
 
 /* ---- chunked output ---- */
 /* model_cloudrun/transferem.py:171-184: re-tiles the uint8 result volume vol[z,y,x] into chunk^3 blocks (clipped at the volume

@@ -33,6 +33,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import itertools
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -676,6 +677,30 @@ def augment(t: np.ndarray, perm, flip, var_adj, mean_adj) -> np.ndarray:
     out = out.astype(np.float32) * np.float32(var_adj)
     out = out + np.float32(mean_adj)
     return np.ascontiguousarray(out.astype(np.float32))
+
+
+def warp_tensor(t: np.ndarray, uniform: np.ndarray, rate: float = 4 / (128 * 128)) -> np.ndarray:
+    """transfer_em/debug.py:7-63 with the random draw made explicit.  t: float32 [Z,Y,X,1] or [Y,X,1] -> conv 'SAME' (zero
+    padding) with ones(3^d)/3^d -> mask = uniform < rate -> conv 'SAME' with ones(4^d) (TF pads 1 before, 2 after: window
+    offsets -1..+2) -> where(mask > 0, mean(blurred), blurred).  fp32 throughout; TF's summation order inside the convolution
+    is not specified, so parity with this restatement is to ~1e-6, not bit-exact (parity unpinned, see the module header)."""
+    nd = t.ndim - 1
+    x = np.asarray(t, np.float32)[..., 0]
+    sp = x.shape
+    w = np.float32(1.0) / np.float32(3 ** nd)
+    xp = np.pad(x, 1)
+    blur = np.zeros(sp, np.float32)
+    for off in itertools.product(range(3), repeat=nd):
+        sl = tuple(slice(o, o + n) for o, n in zip(off, sp))
+        blur = (blur + xp[sl] * w).astype(np.float32)
+    seeds = (np.asarray(uniform, np.float32).reshape(sp) < np.float32(rate))
+    sp_ = np.pad(seeds, [(1, 2)] * nd)
+    hole = np.zeros(sp, bool)
+    for off in itertools.product(range(4), repeat=nd):
+        sl = tuple(slice(o, o + n) for o, n in zip(off, sp))
+        hole |= sp_[sl]
+    mean = np.float32(blur.mean(dtype=np.float64))
+    return np.where(hole, mean, blur).astype(np.float32)[..., None]
 
 
 def get_meanstd(tensors: Sequence[np.ndarray]):

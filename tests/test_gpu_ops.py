@@ -569,3 +569,27 @@ def test_chunk_volume_matches_reference_blocks(tmp_path):
     names = write_ng_chunks(vol, str(tmp_path / "ng"), offset_xyz=(128, 0, 64))
     assert names[0] == "128-192_0-64_64-128" and names[-1] == "192-256_128-192_128-192" and len(names) == 2 * 3 * 2
     assert gzip.decompress(open(tmp_path / "ng" / names[1], "rb").read()) == vol[0:64, 0:64, 64:65].tobytes()
+
+
+def test_device_warp_tensor():
+    """debug.warp_tensor (tem_warp_tensor: box blur + dilated holes at the blurred mean, transfer_em/debug.py:7-63) vs the oracle,
+    3-D and 2-D, with the seeds of the holes given explicitly; accuracy() is the RMSE of debug.py:65-71."""
+    from transfer_em_b200 import debug as D
+    r = np.random.default_rng(77)
+    for sp in ((9, 13, 37), (40, 33)):
+        nd = len(sp)
+        t = r.uniform(-1, 1, sp + (1,)).astype(np.float32)
+        u = r.uniform(0.01, 1, sp).astype(np.float32)
+        for pos in ((0,) * nd, tuple(n // 2 for n in sp), tuple(n - 1 for n in sp)):
+            u[pos] = 0.0
+        got = D.warp_tensor(torch.tensor(t).to(DEV), uniform=u).cpu().numpy()
+        ref = O.warp_tensor(t, u)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-6)
+        assert (got == got[(0,) * nd + (0,)]).sum() >= 2 ** nd + 4 ** nd          # the holes are there
+    # default draw: numpy in, numpy out, hole rate 4 / 128^2
+    big = r.uniform(-1, 1, (64, 64, 64, 1)).astype(np.float32)
+    w = D.warp_tensor(big, rng=np.random.default_rng(3))
+    u = np.random.default_rng(3).uniform(0.0, 1.0, 64 ** 3).astype(np.float32)
+    np.testing.assert_allclose(w, O.warp_tensor(big, u), rtol=0, atol=2e-6)
+    assert abs(D.accuracy(big, w) - float(np.sqrt(np.mean((big - w) ** 2)))) < 1e-6

@@ -176,3 +176,29 @@ def test_augment_oracle_matches_explicit_loops():
                     src[perm[k]] = o[k]
                 ref = np.float32(np.float32(t[src[0], src[1], src[2], 0] * var) + mean)
                 assert out[i0, i1, i2, 0] == ref
+
+
+def test_warp_tensor_oracle_against_torch_convolutions():
+    """oracle.warp_tensor (numpy slices) vs a second restatement of transfer_em/debug.py:7-63 with torch convolutions
+    ('SAME' padding written out: 1/1 for the 3^d blur, 1 before / 2 after for the 4^d dilation), 3-D and 2-D."""
+    import torch.nn.functional as F
+    r = np.random.default_rng(5)
+    for sp in ((7, 9, 11), (12, 10)):
+        nd = len(sp)
+        t = r.uniform(-1, 1, sp + (1,)).astype(np.float32)
+        u = r.uniform(0, 1, sp).astype(np.float32)
+        u[(2,) * nd] = 0.0; u[tuple(n - 1 for n in sp)] = 0.0          # two seeds: one interior, one in the far corner
+        got = O.warp_tensor(t, u)
+        x = torch.tensor(t[..., 0])[None, None]
+        conv = F.conv3d if nd == 3 else F.conv2d
+        blur = conv(x, torch.full((1, 1) + (3,) * nd, 1.0 / 3 ** nd), padding=1)
+        m = (torch.tensor(u) < 4 / (128 * 128)).float()[None, None]
+        dil = conv(F.pad(m, (1, 2) * nd), torch.ones((1, 1) + (4,) * nd))
+        ref = torch.where(dil > 0, blur.mean(), blur)[0, 0].numpy()
+        np.testing.assert_allclose(got[..., 0], ref, rtol=0, atol=2e-6)
+        hole = got[..., 0] == np.float32(got[(2,) * nd + (0,)])
+        assert hole[tuple(slice(0, 4) for _ in sp)].all() and hole.sum() == 4 ** nd + 3 ** nd   # [s-2, s+1] per axis, clipped to [n-3, n-1] at the far corner
+    # no seed: pure blur, interior voxel = mean of its 27 neighbours
+    t = r.uniform(-1, 1, (5, 6, 7, 1)).astype(np.float32)
+    out = O.warp_tensor(t, np.ones((5, 6, 7), np.float32))
+    np.testing.assert_allclose(out[2, 3, 3, 0], t[1:4, 2:5, 2:5, 0].mean(), atol=1e-6)

@@ -74,6 +74,7 @@ _SIGS = {
     "tem_chunk_volume": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32, _P, _P]),
     "tem_augment": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
     "tem_mean_var": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    "tem_warp_tensor": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, _P, _P]),
     "tem_conv_forward": (C.c_int, [C.POINTER(TemConvDesc), _P, _P, _P, _P, C.POINTER(C.c_int32), _P]),
     "tem_conv_dgrad": (C.c_int, [C.POINTER(TemConvDesc), _P, C.c_int, _P, _P, C.c_float, _P, C.c_int, _P]),
     "tem_conv_wgrad": (C.c_int, [C.POINTER(TemConvDesc), _P, _P, C.c_int, _P, _P]),

@@ -320,6 +320,63 @@ cudaError_t launch_mean_var(const float* x, long long n, double* scratch, float*
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// debug.py:7-63 warp_tensor(): 3^d box blur (conv 'SAME', zero padding, filter 1/27 or 1/9), then "holes": every voxel whose
+// 4^d 'SAME' window (offsets -1..+2) holds a seed (uniform < rate) is set to the mean of the blurred tensor.
+// Kernel 1 writes the blurred tensor and its fp64 sum, kernel 2 applies the holes in place.
+// ------------------------------------------------------------------------------------------------
+__global__ void warp_blur_kernel(const float* __restrict__ x, float* __restrict__ out, int Z, int Y, int X, int nd, double* acc) {
+  const long long n = (long long)Z * Y * X;
+  const float w = nd == 3 ? (1.0f / 27.0f) : (1.0f / 9.0f);
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % X); const long long r = i / X; const int yy = (int)(r % Y); const int zz = (int)(r / Y);
+    float a = 0.f;
+    for (int dz = (nd == 3 ? -1 : 0); dz <= (nd == 3 ? 1 : 0); ++dz) {
+      const int z = zz + dz; if (z < 0 || z >= Z) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = yy + dy; if (y < 0 || y >= Y) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int q = xx + dx; if (q < 0 || q >= X) continue;
+          a = fmaf(__ldg(x + ((long long)z * Y + y) * X + q), w, a);
+        }
+      }
+    }
+    out[i] = a; s += (double)a;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double ss[8];
+  if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += ss[k]; atomicAdd(acc, t); }
+}
+__global__ void warp_holes_kernel(float* __restrict__ out, const float* __restrict__ u, int Z, int Y, int X, int nd, float rate, const double* acc) {
+  const long long n = (long long)Z * Y * X;
+  const float mean = (float)(acc[0] / (double)n);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % X); const long long r = i / X; const int yy = (int)(r % Y); const int zz = (int)(r / Y);
+    bool hole = false;
+    for (int dz = (nd == 3 ? -1 : 0); dz <= (nd == 3 ? 2 : 0) && !hole; ++dz) {
+      const int z = zz + dz; if (z < 0 || z >= Z) continue;
+      for (int dy = -1; dy <= 2 && !hole; ++dy) {
+        const int y = yy + dy; if (y < 0 || y >= Y) continue;
+        for (int dx = -1; dx <= 2; ++dx) {
+          const int q = xx + dx; if (q < 0 || q >= X) continue;
+          if (__ldg(u + ((long long)z * Y + y) * X + q) < rate) { hole = true; break; }
+        }
+      }
+    }
+    if (hole) out[i] = mean;
+  }
+}
+cudaError_t launch_warp_tensor(const float* in, const float* uniform, float* out, int Z, int Y, int X, int nd, float rate, double* scratch, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), st); if (e) return e;
+  const long long n = (long long)Z * Y * X;
+  warp_blur_kernel<<<grid_for(n), 256, 0, st>>>(in, out, Z, Y, X, nd, scratch); ++g_tem_launches;
+  warp_holes_kernel<<<grid_for(n), 256, 0, st>>>(out, uniform, Z, Y, X, nd, rate, scratch); ++g_tem_launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_standardize_u8(const uint8_t* in, float* out, long long n, float mean, float stdv, cudaStream_t st) {
   standardize_u8_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, mean, stdv); ++g_tem_launches;
   return cudaGetLastError();

@@ -194,6 +194,7 @@ struct AugmentArgs {     // datasets.py:123-155
 };
 cudaError_t launch_augment(const AugmentArgs& a, cudaStream_t st);
 cudaError_t launch_mean_var(const float* x, long long n, double* scratch /* 2 doubles + 1 uint, zeroed */, float* out, cudaStream_t st);
+cudaError_t launch_warp_tensor(const float* in, const float* uniform, float* out, int Z, int Y, int X, int nd, float rate, double* scratch, cudaStream_t st);
 cudaError_t launch_chunk_volume(const uint8_t* vol, long long Z, long long Y, long long X, int c, uint8_t* out, cudaStream_t st);
 struct StitchArgs {
   const float* y;      // generator output fp32 [T, od+2*tpad, .., 1]

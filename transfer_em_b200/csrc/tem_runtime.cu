@@ -1152,6 +1152,15 @@ extern "C" int tem_mean_var(const float* in, int64_t n, void* scratch, float* ou
   TEM_CUDA(launch_mean_var(in, n, (double*)scratch, out, (cudaStream_t)stream));
   return TEM_OK;
 }
+extern "C" int tem_warp_tensor(const float* in, const float* uniform, float* out, const int32_t dims_zyx[3], int32_t ndims,
+                               float hole_rate, void* scratch, void* stream) {
+  if (!in || !uniform || !out || !dims_zyx || !scratch || in == out) ARG_FAIL("tem_warp_tensor: bad arguments");
+  if (ndims != 2 && ndims != 3) ARG_FAIL("tem_warp_tensor: ndims must be 2 or 3");
+  for (int i = 0; i < 3; ++i) if (dims_zyx[i] < 1) ARG_FAIL("tem_warp_tensor: bad dims");
+  if (ndims == 2 && dims_zyx[0] != 1) ARG_FAIL("tem_warp_tensor: 2-D data is a depth-1 volume");
+  TEM_CUDA(launch_warp_tensor(in, uniform, out, dims_zyx[0], dims_zyx[1], dims_zyx[2], ndims, hole_rate, (double*)scratch, (cudaStream_t)stream));
+  return TEM_OK;
+}
 extern "C" int tem_focal_logits(const float* logits, int64_t n, float target, float gamma, float scale,
                                 float* loss_out, float* grad, void* stream) {
   if (!logits || n <= 0) ARG_FAIL("bad arguments");
