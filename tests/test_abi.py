@@ -79,3 +79,32 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["dimsize"] == 74 and d["config"]["wf"] == 8 and "config 3" in d["config"]["workload"]
+
+
+def test_tf_checkpoint_converter_packs_the_restore_format():
+    """tools/convert_tf_checkpoint.py: its numpy half must write exactly the keys, sizes and variable order
+    that EM2EM.make_checkpoint / restore use (flat vectors in layer order, Keras layouts; 129 480 / 181 369 parameters)."""
+    import importlib.util
+    import numpy as np
+    from oracle import tem_oracle as O
+    spec = importlib.util.spec_from_file_location("convert_tf_checkpoint", os.path.join(ROOT, "tools", "convert_tf_checkpoint.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = np.random.default_rng(0)
+    W = {}
+    for name in mod.NETS:
+        layers = O.generator_layers(8) if name.startswith("generator") else O.discriminator_layers(8, True)
+        W[name] = O.init_params(layers, True, r)
+    m = {k: [np.full_like(a, 0.5) for a in v] for k, v in W.items()}
+    data = mod.pack_checkpoint(W, m, None, step=7, wf=8, is3d=True, dimsize=74)
+    assert int(data["step"]) == 7 and int(data["wf"]) == 8 and int(data["is3d"]) == 1 and int(data["dimsize"]) == 74
+    for name in mod.NETS:
+        n = 129480 if name.startswith("generator") else 181369
+        assert data[name].shape == (n,) and data[name].dtype == np.float32
+        assert data[name + "_optimizer_m"].shape == (n,) and np.all(data[name + "_optimizer_m"] == 0.5)
+        assert data[name + "_optimizer_v"].shape == (n,) and not data[name + "_optimizer_v"].any()
+        off = 0
+        for a in W[name]:                                  # variable order and layout are preserved
+            np.testing.assert_array_equal(data[name][off:off + a.size], np.asarray(a, np.float32).reshape(-1)); off += a.size
+    src = open(os.path.join(ROOT, "transfer_em_b200", "cgan.py")).read()
+    for key in ("_optimizer_m", "_optimizer_v", '"step"', '"wf"', '"is3d"', '"dimsize"'):
+        assert key in src                                  # the reader's keys
