@@ -42,6 +42,7 @@ struct Tc3Args {
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
   uint32_t drop_key;
   int accumulate;
+  int dbg;                     // experiment bit (TEM_S2_DBG & 1): no epilogue conversion / memory traffic
 };
 
 
@@ -165,7 +166,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
     const int oy = y0 + yl, ox = x0 + xl;
-    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ew = (warp - 2) >> 2;                 // 0 / 1: this warp drains the even / odd output slices of its quadrant
     if (ew == 0) {
@@ -337,6 +338,7 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.Cout = a.Cout; t.slope = a.slope;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
   CUtensorMap m0, m1;
   if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
   if (a.C1) { if (!tem_make_map_plane(&m1, &t.merged1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }

@@ -218,7 +218,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         oyv[c4] = 2 * qy + (c4 >> 1) - a.pad; oxv[c4] = 2 * qx + (c4 & 1) - a.pad;
-        ok[c4] = zok && oyv[c4] >= 0 && oyv[c4] < a.L[1] && oxv[c4] >= 0 && oxv[c4] < a.L[2];
+        ok[c4] = zok && oyv[c4] >= 0 && oyv[c4] < a.L[1] && oxv[c4] >= 0 && oxv[c4] < a.L[2] && !(a.dbg & 1);
         if (kPrefetch && ok[c4]) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -389,7 +389,7 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
     const int oy = y0 + yl, ox = x0 + xl;
-    const bool inside = oy < a.L[1] && ox < a.L[2];
+    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
     for (int zo = 0; zo < nz; ++zo) {
       const int oz = z0 + zo;
       uint4 refq[NPAD / 8], accq[NPAD / 8];
