@@ -93,6 +93,35 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
   }
 };
 
+// the same epilogue on a precomputed output pointer / dropout index (index arithmetic hoisted by the caller); LeakyReLU' of
+// the reference is taken from the raw bf16 halves: ref > 0 <=> sign bit clear and magnitude non-zero
+__device__ __forceinline__ void epi_finish(const S2Args& a, float* v, const uint4& rq, const uint4& aq, bf16* op, uint32_t di) {
+  if (a.ref) {
+    const uint32_t w[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!((w[i] & 0x7fffu) != 0u && (w[i] & 0x8000u) == 0u)) v[2 * i] *= a.ref_slope;
+      if (!((w[i] & 0x7fff0000u) != 0u && (w[i] & 0x80000000u) == 0u)) v[2 * i + 1] *= a.ref_slope;
+    }
+  }
+  if (a.drop_key) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] *= 2.f * tem_keep(a.drop_key, di + (uint32_t)u);
+  }
+  if (a.accumulate) {
+    float o[8]; unpack8(aq, o);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] += o[u];
+  }
+  if (a.slope != 1.f) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * a.slope;
+  }
+  uint4 pk;
+  pk.x = pack2(v[0], v[1]); pk.y = pack2(v[2], v[3]); pk.z = pack2(v[4], v[5]); pk.w = pack2(v[6], v[7]);
+  if (!(a.dbg & 32)) *reinterpret_cast<uint4*>(op) = pk;
+}
+
 __device__ __forceinline__ void decode_work(const S2Args& a, int& b, int& x0, int& y0, int& z0, int& nz) {
   int w = blockIdx.x;
   const int zc_i = w % a.nzc; w /= a.nzc;
@@ -206,25 +235,41 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const int rz = (warp - 2) >> 2;                // output z parity handled by this warp
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
-    const int qy = y0 + yl, qx = x0 + xl;
     constexpr int NCH = CP / 8;
     constexpr bool kPrefetch = CP <= 16;           // operands of all four (ry,rx) classes are fetched before the accumulator wait
+    // measured (TEM_S2_DBG=1): this epilogue, not the MMAs or the loads, bounds the kernel (g2.dgrad 49.9 us, 20.2 us without
+    // it), and its cost is index arithmetic: a thread owns ONE q-voxel, so class offsets, validity and z strides are hoisted
+    const int oy0 = 2 * (y0 + yl) - a.pad, ox0 = 2 * (x0 + xl) - a.pad, oz0 = 2 * z0 + rz - a.pad;
+    bool okc[4]; int ooff[4], roff[4]; uint32_t doff[4];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int oy = oy0 + (c4 >> 1), ox = ox0 + (c4 & 1);
+      okc[c4] = !(a.dbg & 1) && oy >= 0 && oy < a.L[1] && ox >= 0 && ox < a.L[2];
+      ooff[c4] = ((c4 >> 1) * a.OX + (c4 & 1)) * a.out_C;
+      roff[c4] = ((c4 >> 1) * a.RX + (c4 & 1)) * a.ref_C;
+      doff[c4] = (uint32_t)(((c4 >> 1) * a.L[2] + (c4 & 1)) * a.Cout);
+    }
+    const long long o_zs = 2LL * a.OY * a.OX * a.out_C, r_zs = 2LL * a.RY * a.RX * a.ref_C;      // two output slices per q-slice
+    bf16* const out0 = a.out + Epi::out_off(a, b, oz0, oy0, ox0);
+    const bf16* const ref0 = a.ref ? a.ref + Epi::ref_off(a, b, oz0, oy0, ox0) : a.out;        // never read when a.ref == nullptr
+    const uint32_t di0 = (uint32_t)(((((long long)b * a.L[0] + oz0) * a.L[1] + oy0) * a.L[2] + ox0) * a.Cout);
+    const uint32_t di_zs = (uint32_t)(2 * a.L[1] * a.L[2] * a.Cout);
     for (int zo = 0; zo < nz; ++zo) {
-      const int qz = z0 + zo;
-      const int oz = 2 * qz + rz - a.pad;
-      const bool zok = oz >= 0 && oz < a.L[0];
-      bool ok[4]; int oyv[4], oxv[4];
+      const int oz = oz0 + 2 * zo;
+      const bool zv = oz >= 0 && oz < a.L[0];
+      bf16* const outz = out0 + zo * o_zs;
+      const bf16* const refz = ref0 + zo * r_zs;
       uint4 refq[kPrefetch ? 4 : 1][NCH], accq[kPrefetch ? 4 : 1][NCH];
+      if (kPrefetch) {
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        oyv[c4] = 2 * qy + (c4 >> 1) - a.pad; oxv[c4] = 2 * qx + (c4 & 1) - a.pad;
-        ok[c4] = zok && oyv[c4] >= 0 && oyv[c4] < a.L[1] && oxv[c4] >= 0 && oxv[c4] < a.L[2] && !(a.dbg & 1);
-        if (kPrefetch && ok[c4]) {
+        for (int c4 = 0; c4 < 4; ++c4) {
+          if (zv && okc[c4]) {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (c * 8 < a.Cout) {
-              if (a.ref) refq[c4][c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8));
-              if (a.accumulate) accq[c4][c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8);
+            for (int c = 0; c < NCH; ++c) {
+              if (c * 8 < a.Cout) {
+                if (a.ref) refq[c4][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
+                if (a.accumulate) accq[c4][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
+              }
             }
           }
         }
@@ -235,12 +280,13 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         __syncwarp();
-        if (!kPrefetch && ok[c4]) {
+        const bool ok = zv && okc[c4];
+        if (!kPrefetch && ok) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             if (c * 8 < a.Cout) {
-              if (a.ref) refq[0][c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8));
-              if (a.accumulate) accq[0][c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oyv[c4], oxv[c4]) + c * 8);
+              if (a.ref) refq[0][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
+              if (a.accumulate) accq[0][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
             }
           }
         }
@@ -252,14 +298,15 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tempty_bar[zo & 1]);
         }
-        if (ok[c4]) {
+        if (ok) {
+          const uint32_t di = di0 + (uint32_t)zo * di_zs + doff[c4];
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             if (c * 8 < a.Cout) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              Epi::run(a, v, c * 8, b, oz, oyv[c4], oxv[c4], refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c]);
+              epi_finish(a, v, refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c], outz + ooff[c4] + c * 8, di + (uint32_t)(c * 8));
             }
           }
         }
