@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: minutes of CPU oracle work next to the GPU run (still part of -m gpu)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -1,0 +1,93 @@
+"""The CUDA path against the golden vectors produced by the reference's own code (tests/golden/ref_*.npz, written by
+tools/make_reference_golden.py: /root/reference/transfer_em run on oracle/tf_shim).  tests/test_reference_golden.py holds
+the oracle to the same files on the CPU.  Tolerances: bit-exact for uint8 / index work; for the bf16 kernels the bands of
+tests/test_gpu_model.py against an fp32 computation (outputs 2e-2, losses 3e-2, gradient direction cos > 0.995 and norm 2 %)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tem_oracle as O
+from tests.gpu_helpers import rel_l2
+from tests.test_reference_golden import gold, inputs_for, on_path, params_for, probes, NETS as NET_KEYS
+from transfer_em_b200 import EM2EM, predict_ng_cube
+from transfer_em_b200 import datasets as D, debug as DBG
+from transfer_em_b200._lib import NET_G, NET_F, NET_DX, NET_DY
+
+pytestmark = pytest.mark.gpu
+NETS = {'g': NET_G, 'f': NET_F, 'dx': NET_DX, 'dy': NET_DY}
+
+
+def _cos(a, b):
+    a = np.asarray(a, np.float64).reshape(-1); b = np.asarray(b, np.float64).reshape(-1)
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
+
+
+def test_uint8_conventions_bit_exact_vs_reference_functions():
+    z = gold("ref_conversions.npz")
+    u = np.arange(256, dtype=np.uint8)
+    for i in range(4):
+        got = D.scale_and_standardize(u, tuple(float(v) for v in z[f"ms_{i}"]))[:, 0]
+        assert np.array_equal(got, z[f"std_{i}"]), i
+    got = D.unstandardize_to_uint8(z["y_sweep"], tuple(float(v) for v in z["ms_y"]))
+    assert np.array_equal(got, z["y_u8"])                 # np.around half-even + the uint8 wrap of utils.py:118
+    r = np.random.default_rng(5)
+    tensors = [r.standard_normal((9, 11, 13, 1)).astype(np.float32) * (1 + 0.1 * i) + 0.01 * i for i in range(5)]
+    np.testing.assert_allclose(np.array(D.get_meanstd(tensors)), z["meanstd"], rtol=5e-6)
+    for nd in (3, 2):
+        w = DBG.warp_tensor(z[f"warp_in_{nd}"], uniform=z[f"warp_uniform_{nd}"])
+        np.testing.assert_allclose(w, z[f"warp_out_{nd}"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(DBG.accuracy(z["warp_in_3"], z["warp_out_3"]), float(z["accuracy"]), rtol=1e-6)
+
+
+def test_predict_ng_cube_vs_reference_predict_ng_cube():
+    z = gold("ref_predict_ng_cube.npz")
+    vol = np.random.default_rng(int(z["vol_seed"])).integers(0, 256, (110, 110, 110), dtype=np.uint8)
+    start, size = tuple(int(v) for v in z["start"]), tuple(int(v) for v in z["size"])
+    ms_x, ms_y = tuple(float(v) for v in z["ms_x"]), tuple(float(v) for v in z["ms_y"])
+    P = params_for(8, True, 33, 5.0)
+    P["g"][11] = (P["g"][11] * np.float32(z["g11_scale"])).astype(np.float32)
+    model = EM2EM(74, "tile_golden", max_batch=4, train=False, checkpoint_dir="/tmp/tem_parity_ckpt_none")
+    model.engine.set_weights(NET_G, P["g"])
+    inb, out = predict_ng_cube(vol, start, size, model, ms_x, ms_y, fetch_input=True)
+    assert out.shape == z["gen_out"].shape and out.dtype == np.uint8
+    assert np.array_equal(inb, z["exact_in"])             # fetch_input: the reference's truncating cast, bit-exact
+    diff = np.abs(out.astype(int) - z["gen_out"].astype(int)); diff = np.minimum(diff, 256 - diff)
+    assert diff.max() <= 2 and (diff > 0).mean() < 0.35   # bf16 generator vs the reference's fp32: +-1 grey level
+
+
+@pytest.mark.parametrize("name", ["2d", "3d", "3d_dropout"])
+def test_train_step_vs_reference_train_step(name):
+    z = gold(f"ref_train_{name}.npz")
+    is3d, B, seed, scale, wf = bool(z["is3d"]), int(z["B"]), int(z["seed"]), float(z["scale"]), int(z["wf"])
+    P = params_for(wf, is3d, seed, scale)
+    rx, ry = inputs_for(is3d, B, seed)
+    keys = [int(k) for k in z["dropout_keys"]] if "dropout_keys" in z.files else None
+    model = EM2EM(74, "golden", is3d=is3d, wf=wf, max_batch=B, dropout=keys is not None, checkpoint_dir="/tmp/tem_parity_ckpt_none")
+    for k, net in NETS.items():
+        model.engine.set_weights(net, P[k])
+    eng = model.engine
+    if keys:
+        eng.set_dropout_keys(keys)
+    losses = eng.train_grads(rx, ry)
+    np.testing.assert_allclose(np.array(losses), z["losses"][0], rtol=3e-2, atol=1e-4)
+    for k, net in NETS.items():
+        got = on_path(k, is3d, eng.get_weights(net, which=1))
+        ref = []
+        for i in range(len(got)):
+            ref.append(z[f"grad_{k}_{i}"] if f"grad_{k}_{i}" in z.files else z[f"grad16_{k}_{i}"].astype(np.float64) * float(z[f"gradmax_{k}_{i}"]))
+        fg = np.concatenate([g.reshape(-1) for g in got]); fr = np.concatenate([g.reshape(-1) for g in ref])
+        assert _cos(fg, fr) > 0.995 and abs(np.linalg.norm(fg) / np.linalg.norm(fr) - 1) < 2e-2, (k, _cos(fg, fr), rel_l2(fg, fr))
+        np.testing.assert_allclose(probes(got)[:, 0].sum(), z[f"grad_probe_{k}"][:, 0].sum(), rtol=3e-2)
+    # the optimizer: the same three steps the reference took (same batch, same injected masks)
+    for step in range(z["losses"].shape[0]):
+        before = {k: eng.get_weights(net) for k, net in NETS.items()}
+        if keys:
+            eng.set_dropout_keys(keys)
+        l = model.train_step(rx, ry)
+        np.testing.assert_allclose(np.array(l), z["losses"][step], rtol=3e-2, atol=1e-4)
+        for k, net in NETS.items():
+            delta = on_path(k, is3d, [a - b for a, b in zip(eng.get_weights(net), before[k])])
+            # Adam's first steps move every weight by ~lr * sign(g): the norm of the update is pinned tightly
+            np.testing.assert_allclose(probes(delta)[:, 0], z[f"delta_{k}_step{step + 1}"][:, 0], rtol=5e-2, atol=1e-9)
+    y = model.predict(rx)
+    assert rel_l2(np.asarray(y)[:1, ::3, ::3], z["predict_after"]) < 2e-2

@@ -499,15 +499,6 @@ def test_single_channel_conv_wide_models():
     np.testing.assert_allclose(dx1, dref1, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 
 
-def test_tma_wgrad_variant_in_subprocess():
-    """The opt-in TMA-ring weight-gradient kernel (TEM_WGRAD_TMA=1) must agree with the oracle too."""
-    import os, subprocess, sys
-    env = dict(os.environ, TEM_WGRAD_TMA="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "tensor_core_wgrad", "-x"],
-                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-2000:]
-
-
 def test_device_augment_bit_exact():
     """datasets.py:123-155 on device: axis shuffle + flips are index work (bit-exact), the intensity jitter is two fp32
     roundings in the reference's order; the uint8 entry fuses scale_tensor + standardize_population in front."""

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtem_b200.so")
-SOURCES = ["tem_runtime.cu", "conv_direct.cu", "elementwise.cu", "conv_tc.cu", "wgrad_mma.cu", "wgrad_c1.cu", "conv_mma.cu", "conv_c1.cu", "wgrad_tma.cu", "conv_tc3.cu", "conv_tc_s2.cu", "wgrad_tc.cu", "conv_tcw.cu", "wgrad_tc_s2.cu", "conv_small.cu", "wgrad_tcw.cu"]
+SOURCES = ["tem_runtime.cu", "conv_direct.cu", "elementwise.cu", "wgrad_mma.cu", "wgrad_c1.cu", "conv_mma.cu", "conv_c1.cu", "conv_tc3.cu", "conv_tc_s2.cu", "wgrad_tc.cu", "conv_tcw.cu", "wgrad_tc_s2.cu", "conv_small.cu", "wgrad_tcw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
 
@@ -29,7 +29,9 @@ def _digest(srcs):
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, ablation=False):
+    if ablation:                      # stage-ablation build (results are wrong by design): never stamped as current
+        NVCC_FLAGS.append("-DTEM_ABLATION"); force = True
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     stamp = LIB + ".stamp"
     dig = _digest(srcs)
@@ -55,4 +57,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablation="--ablation" in sys.argv))

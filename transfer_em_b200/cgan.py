@@ -46,31 +46,38 @@ class EM2EM(object):
         self.meanstd_x, self.meanstd_y = meanstd_x, meanstd_y
         self.rank, self.world = 0, 1
         if distributed:
-            self._init_distributed()
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("distributed=True needs torch.distributed.init_process_group first")
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
         # checkpoints (cgan.py:84-103): own flat format, same directory convention, max_to_keep=50
         self.checkpoint_path = checkpoint_dir or f"./checkpoints/train_{exp_name}"
         self.max_to_keep = 50
-        if ckpt_restore is not None:
-            self.restore(ckpt_restore)
-            print(f"checkpoint {ckpt_restore} restored")
-        else:
-            latest = self.latest_checkpoint()
-            if latest:
-                self.restore(latest)
-                print('Latest checkpoint restored!!')
+        # Restore FIRST, then replicate: rank 0 alone resolves and reads the checkpoint (the directory need not be shared
+        # and must not be listed at different moments by different ranks); tem_comm_sync_params then ships rank 0's
+        # parameters and Adam moments to every replica and the step counter travels beside them.
+        if self.rank == 0:
+            if ckpt_restore is not None:
+                self.restore(ckpt_restore)
+                print(f"checkpoint {ckpt_restore} restored")
+            else:
+                latest = self.latest_checkpoint()
+                if latest:
+                    self.restore(latest)
+                    print('Latest checkpoint restored!!')
+        if distributed:
+            self._init_distributed()
 
     # ---- data parallel (README.md:93-94, cgan.py:8-11) ----------------------------------------
     def _init_distributed(self):
         import torch.distributed as dist
-        if not dist.is_initialized():
-            raise RuntimeError("distributed=True needs torch.distributed.init_process_group first")
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
         def bcast(raw):
             obj = [raw]
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
-        self.engine.init_comm(self.rank, self.world, bcast)
+        self.engine.init_comm(self.rank, self.world, bcast)       # NCCL communicator + broadcast of params / m / v from rank 0
+        self.engine.step = int(bcast(self.engine.step if self.rank == 0 else None))   # Adam bias correction uses the step
 
     # ---- checkpoints ----------------------------------------------------------------------------
     def _ckpts(self):
@@ -83,20 +90,27 @@ class EM2EM(object):
 
     def make_checkpoint(self, epoch_num):
         """cgan.py:105-107: saves the four networks and the four optimizers' state."""
-        os.makedirs(self.checkpoint_path, exist_ok=True)
-        fs = self._ckpts()
-        nxt = (int(os.path.basename(fs[-1])[5:-4]) + 1) if fs else 1
-        path = os.path.join(self.checkpoint_path, f"ckpt-{nxt}.npz")
-        data = {"step": np.int64(self.engine.step), "wf": np.int64(self.engine.wf), "is3d": np.int64(self.is3d),
-                "dimsize": np.int64(self.engine.dimsize)}
-        for name, net in (("generator_g", NET_G), ("generator_f", NET_F), ("discriminator_x", NET_DX), ("discriminator_y", NET_DY)):
-            data[name] = self.engine.get_vector(net, 0)
-            data[name + "_optimizer_m"] = self.engine.get_vector(net, 2)
-            data[name + "_optimizer_v"] = self.engine.get_vector(net, 3)
+        path = None
         if self.rank == 0:
+            os.makedirs(self.checkpoint_path, exist_ok=True)
+            fs = self._ckpts()
+            nxt = (int(os.path.basename(fs[-1])[5:-4]) + 1) if fs else 1
+            path = os.path.join(self.checkpoint_path, f"ckpt-{nxt}.npz")
+            data = {"step": np.int64(self.engine.step), "wf": np.int64(self.engine.wf), "is3d": np.int64(self.is3d),
+                    "dimsize": np.int64(self.engine.dimsize)}
+            for name, net in (("generator_g", NET_G), ("generator_f", NET_F), ("discriminator_x", NET_DX), ("discriminator_y", NET_DY)):
+                data[name] = self.engine.get_vector(net, 0)
+                data[name + "_optimizer_m"] = self.engine.get_vector(net, 2)
+                data[name + "_optimizer_v"] = self.engine.get_vector(net, 3)
             np.savez(path, **data)
             for old in self._ckpts()[:-self.max_to_keep]:
                 os.remove(old)
+        if self.world > 1:       # every rank returns the path rank 0 wrote, and only after it exists
+            import torch.distributed as dist
+            obj = [path]
+            dist.broadcast_object_list(obj, src=0)
+            path = obj[0]
+            dist.barrier()
         print(f"Saving checkpoint for epoch {epoch_num} at {path}")
         return path
 

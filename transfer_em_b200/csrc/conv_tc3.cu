@@ -1,15 +1,15 @@
-// tcgen05 implicit-GEMM 3x3x3 stride-1 convolution, second generation: the three kz taps share one MMA.
+// tcgen05 implicit-GEMM 3x3x3 stride-1 convolution: the three kz taps share one MMA.
 //
-// conv_tc.cu issues, per OUTPUT z-slice, 27*Cin/16 MMAs of shape M128 x N(Cout) x K16; with Cout = 8..32 every one of
-// them re-reads a 4 KB A tile from shared memory for 8-16 cycles of math, and ncu shows the kernel pinned at the
-// shared-memory A-read rate (profiles/README.md).  Here the MMAs are issued per INPUT z-slice instead: an input slice s
+// A per-OUTPUT-slice formulation issues 27*Cin/16 MMAs of shape M128 x N(Cout) x K16 per slice; with Cout = 8..32 every
+// one of them re-reads a 4 KB A tile from shared memory for 8-16 cycles of math and the kernel is pinned at the
+// shared-memory A-read rate (profiles/README.md, round 1).  Here the MMAs are issued per INPUT z-slice instead: an input slice s
 // contributes to the output slices s, s-1, s-2 through the taps kz = 0, 1, 2, so one MMA with
 // N' = 3*CP columns (B = [W(kz=0) | W(kz=1) | W(kz=2)]) accumulates all three at once into three ADJACENT column
 // groups of a TMEM-resident accumulator strip: output slice zo lives at column (ZCAP + 1 - zo) * CP, hence slices
 // s, s-1, s-2 are consecutive.  One third of the MMAs and of the A-operand traffic; every input slice is consumed by
 // exactly one MMA batch (the ring slot is released at once); accumulators of a whole z-chunk stay in TMEM
 // (<= 512 columns), are zeroed once with tcgen05.st and drained slice by slice by the epilogue warps while later
-// slices are still being accumulated.  Everything else (TMA halo planes, descriptors, fused epilogues) is conv_tc.cu's.
+// slices are still being accumulated.
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
@@ -292,6 +292,24 @@ int np_of(int cp) { return cp == 8 ? 32 : 3 * cp; }
 
 }  // namespace
 
+bool tc_conv_supported(const ConvArgs& a) {
+  if (a.form != 0 && !(a.form == 1 && a.stride[0] == 1 && a.stride[1] == 1 && a.stride[2] == 1)) return false;
+  if (a.k[0] != 3 || a.k[1] != 3 || a.k[2] != 3) return false;
+  if (a.stride[0] != 1 || a.stride[1] != 1 || a.stride[2] != 1) return false;
+  if (a.s0.dtype != DT_BF16 || a.out_dtype != DT_BF16) return false;
+  if (a.s0.origins || a.use_lut || a.bias) return false;
+  const int cin = a.C0 + a.C1;
+  if (!(cin == 8 || cin % 16 == 0)) return false;
+  if (a.C0 % 8 || a.C1 % 8 || a.s0.C % 8 || a.s0.coff != 0 || a.s0.C != a.C0) return false;
+  if (a.C1 && (a.s1.dtype != DT_BF16 || a.s1.C % 8 || a.s1.coff != 0 || a.s1.C != a.C1)) return false;
+  if (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8) return false;
+  if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
+  const size_t smem = ((tc3_packed_bytes(cin, a.Cout) + 1023) & ~(size_t)1023) + (size_t)4 * (cin / 8) * PLANE_STRIDE + 1024;
+  if (smem > 200 * 1024) return false;
+  if (a.conv_off[0] || a.conv_off[1] || a.conv_off[2]) return false;
+  return tem_get_encode() != nullptr;
+}
+
 size_t tc3_packed_bytes(int cin, int cout) {
   const int spd = (cin == 8) ? 5 : 9 * (cin / 16);
   return (size_t)spd * np_of(cp_of(cout)) * 32;
@@ -338,7 +356,7 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.Cout = a.Cout; t.slope = a.slope;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
-  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
+  t.dbg = tem_ablation_bits();
   CUtensorMap m0, m1;
   if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
   if (a.C1) { if (!tem_make_map_plane(&m1, &t.merged1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }

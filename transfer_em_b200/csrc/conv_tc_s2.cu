@@ -1187,7 +1187,7 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   CUtensorMap m0;
   t.swz = wide_swizzle();
-  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
+  t.dbg = tem_ablation_bits();
   if (variant == 1) {
     if (t.swz) { if (!make_map_sw128(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 1)) return cudaErrorInvalidValue; }
     else if (!tem_make_map_5d(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue;

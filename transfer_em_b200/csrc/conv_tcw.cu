@@ -331,7 +331,7 @@ cudaError_t launch_conv_tcw(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.Cout = a.Cout; t.slope = a.slope;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
-  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
+  t.dbg = tem_ablation_bits();
   static const int swz = getenv("TEM_TCW_NO_SWIZZLE") ? 0 : 1;             // debug knob: 8-channel plane tiles
   t.swz = swz;
   CUtensorMap m0, m1;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 typedef __nv_bfloat16 bf16;
 
@@ -96,18 +97,26 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 #endif
 
+// Stage-ablation knobs (TEM_S2_DBG bits: skip epilogue work / weight loads / input loads / stores; TEM_DEBUG_GEN_BWD:
+// truncated backward) produce WRONG results by design.  They exist only in builds made with -DTEM_ABLATION
+// (python -m transfer_em_b200.build --ablation); the shipped library ignores the environment variables.
+static inline const char* tem_ablation_env(const char* name) {
+#ifdef TEM_ABLATION
+  return getenv(name);
+#else
+  (void)name; return nullptr;
+#endif
+}
+static inline int tem_ablation_bits() { const char* e = tem_ablation_env("TEM_S2_DBG"); return e ? atoi(e) : 0; }
+
 // launchers (conv_direct.cu)
 cudaError_t launch_conv_direct(const ConvArgs& a, cudaStream_t st);
 cudaError_t launch_wgrad_direct(const WgradArgs& a, cudaStream_t st);
 cudaError_t launch_bias_grad(const void* P, int p_dtype, long long nvox, int C, float* db, cudaStream_t st);
 
-// conv_tc.cu: tcgen05 implicit-GEMM path for 3x3x3 stride-1 convolutions (forward and data gradient)
+// conv_tc3.cu: tcgen05 implicit-GEMM path for 3x3x3 stride-1 convolutions, forward and data gradient (three kz taps
+// per MMA, TMEM-resident accumulator strip)
 bool tc_conv_supported(const ConvArgs& a);
-size_t tc_packed_bytes(int cin, int cout);
-cudaError_t tc_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
-cudaError_t launch_conv_tc(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
-
-// conv_tc3.cu: second-generation tcgen05 kernel (three kz taps per MMA, TMEM-resident accumulator strip)
 size_t tc3_packed_bytes(int cin, int cout);
 cudaError_t tc3_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
@@ -152,10 +161,6 @@ cudaError_t launch_wgrad_tc_s2(const WgradArgs& a, cudaStream_t st);
 // wgrad_tcw.cu: tcgen05 weight gradient of the wide 3x3x3 stride-1 layers (channel planes fill M, one dz per CTA)
 bool wgrad_tcw_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_tcw(const WgradArgs& a, cudaStream_t st);
-
-// wgrad_tma.cu: TMA-staged, z-marching version of the tensor-core weight gradient
-bool wgrad_tma_supported(const WgradArgs& a);
-cudaError_t launch_wgrad_tma(const WgradArgs& a, cudaStream_t st);
 
 // wgrad_c1.cu: weight gradient of the single-channel first / last layers
 bool wgrad_c1_supported(const WgradArgs& a);

@@ -182,12 +182,12 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
 
 static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaStream_t st) {
   if (kind == 3) return tcw_pack_weights(a, dst, st);
-  return kind == 2 ? tc_s2_pack_weights(a, dst, st) : (kind == 1 ? tc_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st));
+  return kind == 2 ? tc_s2_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st);
 }
 static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
-  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? tc_s2_kernel_name(a) : kind == 1 ? "conv3_tc_kernel" : "conv3_tc3_kernel";
+  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? tc_s2_kernel_name(a) : "conv3_tc3_kernel";
   if (kind == 3) return launch_conv_tcw(a, wp, st);
-  return kind == 2 ? launch_conv_tc_s2(a, wp, st) : (kind == 1 ? launch_conv_tc(a, wp, st) : launch_conv_tc3(a, wp, st));
+  return kind == 2 ? launch_conv_tc_s2(a, wp, st) : launch_conv_tc3(a, wp, st);
 }
 
 // conv dispatch: tcgen05 implicit GEMM when the shape allows, direct kernel otherwise
@@ -196,13 +196,12 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   for (int ax = 0; ax < 3; ++ax) if (a.L[ax] <= 0) return TEM_OK;
   static const bool no_tc = getenv("TEM_NO_CONV_TC") != nullptr;   // debug knob
   static const bool no_s2 = getenv("TEM_NO_CONV_TC_S2") != nullptr;   // debug knob: stride-2 layers on the mma.sync kernel
-  static const bool gen1 = getenv("TEM_CONV_TC_GEN1") != nullptr;   // debug knob: first-generation kernel (one MMA batch per output slice)
   int kind = -1;                                                    // packed-weight tcgen05 kernels
-  if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) kind = gen1 ? 1 : 0;
+  if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) kind = 0;
   else if (h->cfg.use_tensor_cores && !no_tc && tcw_conv_supported(a)) kind = 3;
   else if (h->cfg.use_tensor_cores && !no_tc && !no_s2 && tc_s2_supported(a)) kind = 2;
   if (kind >= 0) {
-    const size_t bytes = kind == 3 ? tcw_packed_bytes(a.C0 + a.C1, a.Cout) : kind == 2 ? tc_s2_packed_bytes(a) : (kind == 1 ? tc_packed_bytes(a.C0 + a.C1, a.Cout) : tc3_packed_bytes(a.C0 + a.C1, a.Cout));
+    const size_t bytes = kind == 3 ? tcw_packed_bytes(a.C0 + a.C1, a.Cout) : kind == 2 ? tc_s2_packed_bytes(a) : tc3_packed_bytes(a.C0 + a.C1, a.Cout);
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
       static bool pool_kept = false;       // keep freed blocks in the default pool across synchronisations
@@ -221,14 +220,23 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
     }
     auto key = std::make_tuple(a.w, a.form, a.Cout);
     auto it = h->packed.find(key);
+    bool fresh = false;
     if (it == h->packed.end()) {
       tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a; p.kind = kind;
       TEM_CHECK(dev_alloc(h, (void**)&p.buf, bytes));
       it = h->packed.emplace(key, p).first;
+      fresh = true;
     }
     if (it->second.version != h->params_version) {
       TEM_CUDA(pack_tc_weights(kind, a, it->second.buf, st));
       it->second.version = h->params_version;
+      if (h->in_overlap) {
+        // a key first seen inside an overlapped step (e.g. a larger batch selects another kernel variant): the image is
+        // shared by all four streams, so the other three must not run ahead of this pack
+        (void)fresh;
+        TEM_CUDA(cudaEventRecord(h->ev[11], st));
+        for (int i = 0; i < 4; ++i) if (h->aux[i] && h->aux[i] != st) TEM_CUDA(cudaStreamWaitEvent(h->aux[i], h->ev[11], 0));
+      }
     }
     TEM_CUDA(launch_tc_kind(kind, a, it->second.buf, st));
     return TEM_OK;
@@ -347,15 +355,12 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     double macs = (L.transposed ? xvox : dvox) * ci_cnt * L.cout * taps;
     ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
     static const bool no_mma = getenv("TEM_NO_WGRAD_MMA") != nullptr, no_c1 = getenv("TEM_NO_WGRAD_C1") != nullptr;   // debug knobs
-    // TMA-ring variant (wgrad_tma.cu): measured slower than the cp.async tiles at wf=8 (profiles/README.md), opt-in
-    static const bool use_tma = getenv("TEM_WGRAD_TMA") != nullptr;
     static const bool no_wtc = getenv("TEM_NO_WGRAD_TC") != nullptr;   // debug knob: 3x3x3 weight gradients on the mma.sync kernel
     // a kernel that cannot tile the shape (shared memory) answers cudaErrorInvalidConfiguration: the next one is tried
     cudaError_t e = cudaErrorInvalidConfiguration;
     if (h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_supported(a)) { e = launch_wgrad_tc(a, st); g_tem_last_kernel = "wgrad_tc_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_s2_supported(a)) { e = launch_wgrad_tc_s2(a, st); g_tem_last_kernel = "wgrad_tc_s2_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tcw_supported(a)) { e = launch_wgrad_tcw(a, st); g_tem_last_kernel = "wgrad_tcw_kernel"; }
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && use_tma && wgrad_tma_supported(a)) { e = launch_wgrad_tma(a, st); g_tem_last_kernel = "wgrad_tma_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) { e = launch_wgrad_mma(a, st); g_tem_last_kernel = "wgrad_mma_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) { e = launch_wgrad_c1(a, st); g_tem_last_kernel = "wgrad_c1_kernel"; }
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_wgrad_direct(a, st); g_tem_last_kernel = "wgrad_direct_kernel"; }
@@ -610,7 +615,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   TEM_CUDA(cudaSetDevice(cfg->device));
   tem_handle* h = new tem_handle();
   h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
-  h->keys_overridden = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
+  h->keys_overridden = false; h->in_overlap = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
   for (int i = 0; i < 4; ++i) h->aux[i] = nullptr; for (int i = 0; i < 12; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
   h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
   h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
@@ -868,11 +873,12 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   // kernels of this network are latency- rather than bandwidth-bound at wf=8, so overlapping two passes fills the SMs.
   // The first step of a handle (cold packed-weight cache), profiled steps and TEM_NO_OVERLAP=1 run on one stream.
   static const bool no_overlap = getenv("TEM_NO_OVERLAP") != nullptr;
-  static const char* lim_s = getenv("TEM_DEBUG_GEN_BWD");
+  static const char* lim_s = tem_ablation_env("TEM_DEBUG_GEN_BWD");
   const bool overlap = h->overlap_ready && !h->prof.on && !no_overlap && !lim_s;
   cudaStream_t sA = overlap ? h->aux[0] : st, sB = overlap ? h->aux[1] : st, sC = overlap ? h->aux[2] : st, sD = overlap ? h->aux[3] : st;
   cudaStream_t ss[4] = {sA, sB, sC, sD};
   const int setB = overlap ? 1 : 0, setC = overlap ? 2 : 0, setD = overlap ? 3 : 0;
+  h->in_overlap = overlap;
   if (overlap) {
     // packed weight images are shared by all streams: refresh all of them before the fork
     for (auto& kv : h->packed)
@@ -949,7 +955,8 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   if (overlap) {
     for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[6 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[6 + i], 0)); }
   }
-  h->overlap_ready = !h->packed.empty() || !h->cfg.use_tensor_cores;
+  h->in_overlap = false;
+  h->overlap_ready = true;      // the packed-weight cache (if this model has one: 2-D models do not) is warm now
   return TEM_OK;
 }
 

@@ -94,13 +94,14 @@ struct tem_handle {
   int last_gen_net, last_disc_net;
   Profiler prof;
   // packed bf16 UMMA weight images, keyed by (weight pointer, form, columns); re-packed when params change
-  struct Packed { bf16* buf; size_t bytes; uint64_t version; ConvArgs args; int kind; };   // kind: 0 conv_tc3, 1 conv_tc (gen 1), 2 conv_tc_s2, 3 conv_tcw
+  struct Packed { bf16* buf; size_t bytes; uint64_t version; ConvArgs args; int kind; };   // kind: 0 conv_tc3, 2 conv_tc_s2, 3 conv_tcw
   std::map<std::tuple<const float*, int, int>, Packed> packed;
   uint64_t params_version;
   // four internal streams overlap the independent passes of a train step (G(real_x) || F(real_y), ...)
   cudaStream_t aux[4];
   cudaEvent_t ev[12];
   bool overlap_ready;
+  bool in_overlap;              // a train step is between its stream fork and join
 };
 
 struct ProfScope {

@@ -278,7 +278,7 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& w, cudaStream_t st) {
   const int ra = t.s2 ? RB + 1 : (t.split_dy ? RB : RA);
   t.xa_bytes = (t.M / 8) * ra * WA * 16; t.gb_bytes = (t.nb / 8) * RB * WB * 16;
   t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
-  { static const char* dbg = getenv("TEM_S2_DBG"); t.dbg = dbg ? atoi(dbg) : 0; }
+  t.dbg = tem_ablation_bits();
   t.nrg = (w.L[1] + RB - 1) / RB; t.ncb = (w.L[2] + WB - 1) / WB;
   const int gy = (t.s2 ? 16 : (t.split_dy ? 9 : 3)) * t.n_ca * t.n_cb;
   int gx = 148 / gy; if (gx < 1) gx = 1;

@@ -22,6 +22,8 @@ def _as_device(x, device, dtypes=(torch.float32, torch.uint8)):
         t = torch.as_tensor(np.asarray(x))
         was_np = True
     if t.dtype not in dtypes:
+        if torch.float32 not in dtypes:      # byte kernels read raw uint8: never reinterpret another dtype
+            raise TypeError(f"expected a {' / '.join(str(d) for d in dtypes)} array, got {t.dtype}")
         t = t.to(torch.float32)
     if t.device.type != "cuda":
         t = t.to(device, non_blocking=True)
