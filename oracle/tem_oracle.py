@@ -241,8 +241,12 @@ Quant = Optional[Callable[[torch.Tensor], torch.Tensor]]
 
 
 def apply_layer(L: LayerSpec, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor],
-                is3d: bool, training: bool, mask: Optional[torch.Tensor]) -> torch.Tensor:
-    """One layer on NC... tensors.  mask is the dropout keep-mask (NC... layout)."""
+                is3d: bool, training: bool, mask: Optional[torch.Tensor],
+                sign_ref: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One layer on NC... tensors.  mask is the dropout keep-mask (NC... layout).
+    sign_ref (NC... layout, optional): take the LeakyReLU branch of every element from the sign of this externally stored
+    activation instead of from the freshly computed pre-activation (test hook: "evaluate at the stored values" extended to
+    the activation signs; it only matters for pre-activations within rounding noise of zero)."""
     if L.kind == 'conv':
         f = F.conv3d if is3d else F.conv2d
         y = f(x, _w_conv(w), bias=b, stride=L.stride)             # VALID
@@ -253,6 +257,8 @@ def apply_layer(L: LayerSpec, x: torch.Tensor, w: torch.Tensor, b: Optional[torc
     if L.dropout and training:
         if mask is not None:
             y = y * mask * 2.0                                     # Dropout(0.5): keep, scale 1/(1-p)
+    if sign_ref is not None and L.slope != 1.0:
+        return y * torch.where(sign_ref > 0, torch.ones_like(y), torch.full_like(y, L.slope))
     return lrelu(y, L.slope)
 
 
@@ -319,8 +325,10 @@ def generator_forward(params: Sequence[torch.Tensor], x_cl: torch.Tensor, wf: in
 
 def discriminator_forward(params: Sequence[torch.Tensor], x_cl: torch.Tensor, wf: int = 8,
                           is3d: bool = True, quant: Quant = None, qweights: bool = False,
-                          acts: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
-    """discriminator.py:14-105 (disc_prior=None).  params order: d0..d8 kernels, d8 bias last."""
+                          acts: Optional[Dict[str, torch.Tensor]] = None,
+                          sign_acts: Optional[Dict[str, np.ndarray]] = None) -> torch.Tensor:
+    """discriminator.py:14-105 (disc_prior=None).  params order: d0..d8 kernels, d8 bias last.
+    sign_acts: {layer name: stored channels-last activation} -> apply_layer(sign_ref=...) for those layers."""
     layers = discriminator_layers(wf, is3d)
     q = quant if quant is not None else (lambda t: t)
     W = [bf16_round(p) if qweights else p for p in params[:9]]
@@ -330,7 +338,10 @@ def discriminator_forward(params: Sequence[torch.Tensor], x_cl: torch.Tensor, wf
     t = x
     for i in range(start, 9):
         L = layers[i]
-        t = apply_layer(L, t, W[i], bias if L.bias else None, is3d, True, None)
+        sr = None
+        if sign_acts is not None and L.name in sign_acts:
+            sr = _to_nc(torch.as_tensor(np.asarray(sign_acts[L.name]), dtype=t.dtype))
+        t = apply_layer(L, t, W[i], bias if L.bias else None, is3d, True, None, sign_ref=sr)
         if i != 8:
             t = q(t)
         if acts is not None:
@@ -431,7 +442,8 @@ def train_step_grads(P: Dict[str, List[np.ndarray]], real_x: np.ndarray, real_y:
                      loss_mode: str = 'focal', dtype=torch.float64, literal: bool = False,
                      quant: Quant = None, qweights: bool = False,
                      keep_outputs: bool = False,
-                     override_fakes: Optional[Dict[str, np.ndarray]] = None) -> StepResult:
+                     override_fakes: Optional[Dict[str, np.ndarray]] = None,
+                     disc_signs: Optional[Dict[str, Dict[str, np.ndarray]]] = None) -> StepResult:
     """Forward + gradients of cgan.py:148-215.  P = {'g','f','dx','dy'} parameter lists.
 
     masks: {pass_name: {'g6': keep, 'g9': keep}} for pass_name in
@@ -461,11 +473,13 @@ def train_step_grads(P: Dict[str, List[np.ndarray]], real_x: np.ndarray, real_y:
         m = mk(name)
         return generator_forward(T['f'], x, wf, is3d, training=m is not None, masks=m, quant=quant, qweights=qweights)
 
-    def Dx(x):
-        return discriminator_forward(T['dx'], x, wf, is3d, quant=quant, qweights=qweights)
+    ds = disc_signs or {}     # {'dx_real' | 'dy_real' | 'dx_fake' | 'dy_fake': {layer: stored activation}} (see apply_layer)
 
-    def Dy(x):
-        return discriminator_forward(T['dy'], x, wf, is3d, quant=quant, qweights=qweights)
+    def Dx(x, which):
+        return discriminator_forward(T['dx'], x, wf, is3d, quant=quant, qweights=qweights, sign_acts=ds.get('dx_' + which))
+
+    def Dy(x, which):
+        return discriminator_forward(T['dy'], x, wf, is3d, quant=quant, qweights=qweights, sign_acts=ds.get('dy_' + which))
 
     def subst(name, t):
         # test hook: evaluate the downstream graph at externally supplied values of a fake (straight-through
@@ -486,8 +500,8 @@ def train_step_grads(P: Dict[str, List[np.ndarray]], real_x: np.ndarray, real_y:
     rx_c = crop_cl(rx, buf)
     same_y = G(ry, 'g_realy')                            # :181
     ry_c = crop_cl(ry, buf)
-    d_real_x = Dx(rx_c); d_real_y = Dy(ry_c)             # :185-186
-    d_fake_x = Dx(fake_x); d_fake_y = Dy(fake_y)         # :188-189
+    d_real_x = Dx(rx_c, 'real'); d_real_y = Dy(ry_c, 'real')             # :185-186
+    d_fake_x = Dx(fake_x, 'fake'); d_fake_y = Dy(fake_y, 'fake')         # :188-189
 
     if loss_mode == 'focal':
         gen_g = generator_loss(d_fake_y, gamma); gen_f = generator_loss(d_fake_x, gamma)

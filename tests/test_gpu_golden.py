@@ -87,7 +87,9 @@ def test_train_step_vs_reference_train_step(name):
         np.testing.assert_allclose(np.array(l), z["losses"][step], rtol=3e-2, atol=1e-4)
         for k, net in NETS.items():
             delta = on_path(k, is3d, [a - b for a, b in zip(eng.get_weights(net), before[k])])
-            # Adam's first steps move every weight by ~lr * sign(g): the norm of the update is pinned tightly
-            np.testing.assert_allclose(probes(delta)[:, 0], z[f"delta_{k}_step{step + 1}"][:, 0], rtol=5e-2, atol=1e-9)
+            # Adam's first steps move a weight by lr * g / (|g| + 1e-7): ~lr * sign(g) where |g| >> eps (the update norm is then
+            # pinned tightly), but proportional to g where gradient elements are ~1e-7 -- the discriminators' deep kernels at this
+            # weight scale -- so there the bf16 gradient error (and a tail sign flip, see test_gpu_model._disc_tail_signs) shows
+            np.testing.assert_allclose(probes(delta)[:, 0], z[f"delta_{k}_step{step + 1}"][:, 0], rtol=5e-2 if k in ("g", "f") else 0.25, atol=1e-9)
     y = model.predict(rx)
     assert rel_l2(np.asarray(y)[:1, ::3, ::3], z["predict_after"]) < 2e-2

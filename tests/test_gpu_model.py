@@ -124,6 +124,39 @@ def _cos(a, b):
     return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
 
 
+def _disc_tail_signs(engine, rx, ry, ov, P, wf, is3d, layers=(4, 5, 6, 7)):
+    """The stored activations of the discriminators' small tail layers (d4..d7: 6^3 .. 1 voxels in 3-D) for the four D passes
+    of the step, re-run through the deterministic forward API.  A 3-D discriminator ends in ONE voxel per sample: its 32 + 32
+    tail activations gate the whole backward pass through LeakyReLU' (slope 0.09 / 0.3 vs 1), so a single pre-activation that
+    lies within bf16 noise of zero (|v| < ~5e-3 of the typical magnitude: measured with tools/diag_wf4_dy.py, one flip among
+    the 32 values of d6 moved every upstream gradient of that network by 20 %) decides a fifth of the gradient.  "Evaluated at
+    the stored values" therefore includes the stored SIGNS of those layers (apply_layer(sign_ref=...)); the flips found
+    are returned and printed so that the claim is checkable: every flipped element must be a near-zero pre-activation."""
+    b = (rx.shape[1] - ov['fake_y'].shape[1]) // 2
+    crop = (slice(None),) + (slice(b, -b),) * (rx.ndim - 2) + (slice(None),)
+    inputs = {'dx_real': (NET_DX, 'dx', rx[crop]), 'dy_real': (NET_DY, 'dy', ry[crop]),
+              'dx_fake': (NET_DX, 'dx', ov['fake_x']), 'dy_fake': (NET_DY, 'dy', ov['fake_y'])}
+    signs, flips = {}, {}
+    for name, (net, key, x) in inputs.items():
+        x = np.ascontiguousarray(x, np.float32)
+        engine.disc_forward(net, x)
+        acts = {}
+        with torch.no_grad():
+            O.discriminator_forward(_tt(P, key), torch.tensor(x), wf, is3d, quant=O.bf16_round, qweights=True, acts=acts)
+        signs[name] = {}
+        for li in layers:
+            ref = acts[f'd{li}'].numpy()
+            got = engine.last_activation(net, li).reshape(ref.shape)
+            signs[name][f'd{li}'] = got
+            bad = (got > 0) != (ref > 0)
+            if bad.any():
+                flips[(name, li)] = int(bad.sum())
+                assert np.abs(ref[bad]).max() < 2e-2 * np.abs(ref).mean(), (name, li)     # only near-zero values may flip
+    if flips:
+        print("LeakyReLU' sign flips in the discriminator tails (near-zero pre-activations):", flips)
+    return signs, flips
+
+
 def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol=3 * TOL, wf=8, grad_tol=TOL, var_tol=8 * TOL,
                 repeat=1, keys=None):
     """Forward outputs and losses are compared with the plain fp32 oracle (north-star tolerance 1e-2; the loss
@@ -151,8 +184,9 @@ def _check_step(model, P, rx, ry, is3d, masks=None, loss_mode='focal', loss_rtol
         assert rel_l2(model.engine.train_output(name), ref.outputs[name]) < 3 * TOL, name
     np.testing.assert_allclose(np.array(losses), np.array(ref.losses), rtol=loss_rtol, atol=1e-4)
     ov = {'fake_y': model.engine.train_output('fake_y'), 'fake_x': model.engine.train_output('fake_x')}
+    signs, tail_flips = _disc_tail_signs(model.engine, rx, ry, ov, P, wf, is3d)
     refq = O.train_step_grads(P, rx, ry, wf, is3d, masks=masks, dtype=torch.float32, loss_mode=loss_mode,
-                              quant=O.bf16_round, qweights=True, override_fakes=ov, keep_outputs=True)
+                              quant=O.bf16_round, qweights=True, override_fakes=ov, keep_outputs=True, disc_signs=signs)
     for name in ("fake_y", "cycled_x", "fake_x", "cycled_y", "same_x", "same_y"):
         assert rel_l2(model.engine.train_output(name), refq.outputs[name]) < 8e-3, name
     np.testing.assert_allclose(np.array(losses), np.array(refq.losses), rtol=1e-2, atol=1e-5)
@@ -203,7 +237,7 @@ def test_train_step_gradients_config4_width():
     """wf = 1 (64 / 128 / 256 channels: the BASELINE config 4 model) at n = 74, batch 1: the whole train step on the wide
     tcgen05 kernels against the oracle (about 10 TFLOP of CPU work for the two oracle evaluations)."""
     model, P, rx, ry = _train_case(True, 1, False, 35, scale=1.0, wf=1)
-    _, _, worst = _check_step(model, P, rx, ry, True, wf=1, grad_tol=2 * TOL, var_tol=0.25)
+    _, _, worst = _check_step(model, P, rx, ry, True, wf=1)
     print("wf=1 gradient rel-L2 per network:", worst)
 
 
@@ -211,13 +245,12 @@ def test_train_step_gradients_wide_model():
     """wf = 4 (16 / 32 / 64 channels; d4 64 -> 64, g6 64 -> 32): the train step on the wide-layer kernels -- conv_upw_tc /
     conv_downw_tc (streamed weights, swizzled tiles), conv3_tcw, wgrad_tcw in both forms -- against the same oracle."""
     model, P, rx, ry = _train_case(True, 1, False, 27, scale=1.5, wf=4)
-    # per-network gradient band 2e-2 here: measured g / f / d_x < 1e-2, d_y 1.4e-2 (one logit per sample behind 64-channel
-    # layers whose K = 4096 sums sit closer to the bf16 rounding boundaries of the stored activations; see _check_step)
-    # single variables: 0.25 (measured worst: d_y's first-layer kernel, 432 values behind ONE logit at batch 1, 0.20).  Measured
-    # per network: g 8e-4, f 1e-3, d_x 1e-3, d_y 1.4e-2 -- d_x runs the same kernels on the other domain, and the d_y figure is
-    # identical before and after the weight-gradient kernels changed, which points at a LeakyReLU' sign flip in the one-voxel
-    # tail of d_y (see _check_step) rather than at a kernel; not isolated further this round.
-    _, _, worst = _check_step(model, P, rx, ry, True, wf=4, grad_tol=2 * TOL, var_tol=0.25)
+    # Round 1 measured d_y at 1.4e-2 here (0.20 on each of d0..d6) and allowed it.  tools/diag_wf4_dy.py isolated it (round 2,
+    # gpurun_out/diag_wf4_dy.txt): in D_y(real_y) exactly ONE of the 32 activations of the one-voxel layer d6 has the other
+    # sign on the GPU (reference value 2.4e-5 against a typical 4e-3, i.e. inside the bf16 noise of the 20 stored layers in
+    # front of it); LeakyReLU' of d6 is 0.09 vs 1, so that single gate scales everything upstream.  No kernel is involved:
+    # with the stored signs of the tail handed to the oracle (_disc_tail_signs) the standard tolerances hold.
+    _, _, worst = _check_step(model, P, rx, ry, True, wf=4)
     print("wide-model gradient rel-L2 per network:", worst)
 
 

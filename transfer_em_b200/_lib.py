@@ -8,6 +8,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtem_b200.so")
+if os.environ.get("TEM_ABLATION_LIB") == "1":      # profiling tools only: the -DTEM_ABLATION build (python -m transfer_em_b200.build --ablation)
+    LIB_PATH = os.path.join(_HERE, "libtem_b200_abl.so")
 
 TEM_U8, TEM_BF16, TEM_F32 = 0, 1, 2
 NET_G, NET_F, NET_DX, NET_DY = 0, 1, 2, 3

@@ -36,13 +36,15 @@ struct Tc3Args {
   int cin8;                    // 1 when Cin == 8 (tap-pair k-steps)
   const bf16* wpacked; int wbytes;
   int ntx, nty, nzc, zc, zcap, tmem_cols, ring;
+  int items, nbmax;            // work items (persistent CTAs loop over them), pipeline steps of the longest item
+  int sb;                      // input slices per pipeline step: one full / empty / tfull barrier round trip per sb slices
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
   int Cout;
   float slope;
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
   uint32_t drop_key;
   int accumulate;
-  int dbg;                     // experiment bit (TEM_S2_DBG & 1): no epilogue conversion / memory traffic
+  int dbg;                     // stage-ablation bits (-DTEM_ABLATION builds only): 1 no epilogue work, 4 no input loads, 16 no MMAs
 };
 
 
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
   constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[RING3_MAX], empty_bar[RING3_MAX], w_bar, tzero_bar, tfull_bar[kMaxChunk];
+  __shared__ uint64_t full_bar[RING3_MAX], empty_bar[RING3_MAX], w_bar, strip_bar, tfull_bar[kMaxChunk];
   const int RING3 = a.ring;
   __shared__ uint32_t tmem_base_s;
 
@@ -64,22 +66,28 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   const uint32_t wbytes_pad = (uint32_t)((a.wbytes + 1023) & ~1023);
   uint8_t* wsm = smem;
   uint8_t* ring = smem + wbytes_pad;
-  const uint32_t slot_bytes = (uint32_t)planes * PLANE_STRIDE;
+  const int SB = a.sb;
+  const uint32_t slice_bytes = (uint32_t)planes * PLANE_STRIDE;
+  const uint32_t slot_bytes = (uint32_t)SB * slice_bytes;
 
-  // work item
-  int w = blockIdx.x;
-  const int zc_i = w % a.nzc; w /= a.nzc;
-  const int tx_i = w % a.ntx; w /= a.ntx;
-  const int ty_i = w % a.nty; w /= a.nty;
-  const int b = w;
-  const int x0 = tx_i * TX, y0 = ty_i * TY, z0 = zc_i * a.zc;
-  const int nz = min(a.zc, a.L[0] - z0);
-  const int nslices = nz + 2;
+  // Persistent CTAs (two per SM): TMEM allocation, barrier set-up, the weight image and the first zeroing of the
+  // accumulator strip are paid once per CTA, not once per work item; the TMA producer runs ahead into the next item while
+  // the epilogue still drains the current one.  Work item = (sample, y tile, x tile, z chunk), item k of this CTA is
+  // blockIdx.x + k * gridDim.x.  (Stage ablation of the one-item-per-CTA version, profiles/ablation_r2.txt: 25 of 52 us
+  // remained on g1 with loads, MMAs and epilogue work all switched off -- four rounds of CTA start-up and drain.)
+  auto decode = [&](int it, int& b, int& x0, int& y0, int& z0, int& nz) {
+    int w = it;
+    const int zc_i = w % a.nzc; w /= a.nzc;
+    const int tx_i = w % a.ntx; w /= a.ntx;
+    const int ty_i = w % a.nty; w /= a.nty;
+    b = w; x0 = tx_i * TX; y0 = ty_i * TY; z0 = zc_i * a.zc;
+    nz = min(a.zc, a.L[0] - z0);
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING3; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&w_bar, 1); mbar_init(&tzero_bar, 128);
-    for (int i = 0; i < nz; ++i) mbar_init(&tfull_bar[i], 1);
+    mbar_init(&w_bar, 1); mbar_init(&strip_bar, 8);           // one arrival per epilogue warp
+    for (int i = 0; i < a.nbmax; ++i) mbar_init(&tfull_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -91,71 +99,91 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
+  // Pipeline granularity.  Measured on B200 (tools/ubench/sync_latency.cu): one producer -> MMA -> epilogue hand-over
+  // (mbarrier wait + tcgen05.commit x 2 + loop) costs the issuing warp 290-390 cycles however deep the ring is, while the
+  // five N = 32 MMAs of a Cin = 8 slice keep the tensor pipe busy for ~180.  A pipeline step therefore covers SB input
+  // slices (>= ~24 MMAs): one expect_tx / full wait / empty commit / tfull commit per step.
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
       bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
       int slot = 0; uint32_t ph = 0;
-      for (int s = 0; s < nslices; ++s) {
-        mbar_wait(&empty_bar[slot], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * PLANE_BYTES);
-        uint8_t* dst = ring + (size_t)slot * slot_bytes;
-        for (int p = 0; p < a.planes0; ++p)
-          tma_load_plane(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], a.merged0, p, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
-        for (int p = 0; p < a.planes1; ++p)
-          tma_load_plane(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], a.merged1, p, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
-        if (++slot == RING3) { slot = 0; ph ^= 1u; }
+      for (int it = blockIdx.x; it < a.items; it += gridDim.x) {
+        int b, x0, y0, z0, nz; decode(it, b, x0, y0, z0, nz);
+        const int nslices = nz + 2, nbatch = (nslices + SB - 1) / SB;
+        for (int bt = 0; bt < nbatch; ++bt) {
+          const int s0 = bt * SB, n_in = min(SB, nslices - s0);
+          mbar_wait(&empty_bar[slot], ph ^ 1u);
+          if (a.dbg & 4) { mbar_arrive(&full_bar[slot]); if (++slot == RING3) { slot = 0; ph ^= 1u; } continue; }
+          mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(n_in * planes) * PLANE_BYTES);
+          for (int i = 0; i < n_in; ++i) {
+            uint8_t* dst = ring + (size_t)slot * slot_bytes + (size_t)i * slice_bytes;
+            const int s = s0 + i;
+            for (int p = 0; p < a.planes0; ++p)
+              tma_load_plane(dst + p * PLANE_STRIDE, &map0, &full_bar[slot], a.merged0, p, x0 + a.shift0[2], y0 + a.shift0[1], z0 + s + a.shift0[0], b);
+            for (int p = 0; p < a.planes1; ++p)
+              tma_load_plane(dst + (a.planes0 + p) * PLANE_STRIDE, &map1, &full_bar[slot], a.merged1, p, x0 + a.shift1[2], y0 + a.shift1[1], z0 + s + a.shift1[0], b);
+          }
+          if (++slot == RING3) { slot = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     // The whole warp runs the issue loop convergently, so descriptors and barrier addresses stay in uniform registers;
-    // one elected lane issues the MMAs / commits of a slice (no per-instruction election loops in the SASS).
-    {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      mbar_wait(&w_bar, 0);
-      mbar_wait(&tzero_bar, 0);                     // accumulator strip has been zeroed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t wbase = smem_u32(wsm);
-      const uint32_t rbase = smem_u32(ring);
-      // descriptor words: only the start-address field (low 14 bits of the low word, 16 B units) changes per MMA
-      const uint32_t a_hi = ((uint32_t)(HX * 16) >> 4) | (1u << 14);          // SBO = one halo row, version 1
-      const uint32_t b_hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B between n-groups
-      const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;                // LBO = NP*16 B between the K halves
-      const uint32_t a_lbo_planes = ((uint32_t)PLANE_STRIDE >> 4) << 16;      // Cin >= 16: K halves are two planes
-      const uint32_t wb16 = wbase >> 4;
-      const int kcs = planes >> 1;
-      int slot = 0; uint32_t ph = 0;
-      for (int s = 0; s < nslices; ++s) {
+    // one elected lane issues the MMAs / commits of a step (no per-instruction election loops in the SASS).
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(&w_bar, 0);
+    const uint32_t wbase = smem_u32(wsm);
+    const uint32_t rbase = smem_u32(ring);
+    // descriptor words: only the start-address field (low 14 bits of the low word, 16 B units) changes per MMA
+    const uint32_t a_hi = ((uint32_t)(HX * 16) >> 4) | (1u << 14);          // SBO = one halo row, version 1
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);                         // SBO = 128 B between n-groups
+    const uint32_t b_lbo = ((uint32_t)(NP * 16) >> 4) << 16;                // LBO = NP*16 B between the K halves
+    const uint32_t a_lbo_planes = ((uint32_t)PLANE_STRIDE >> 4) << 16;      // Cin >= 16: K halves are two planes
+    const uint32_t wb16 = wbase >> 4;
+    const int kcs = planes >> 1;
+    int slot = 0; uint32_t ph = 0, item_ph = 0;
+    for (int it = blockIdx.x; it < a.items; it += gridDim.x) {
+      int b, x0, y0, z0, nz; decode(it, b, x0, y0, z0, nz);
+      const int nslices = nz + 2, nbatch = (nslices + SB - 1) / SB;
+      mbar_wait(&strip_bar, item_ph); item_ph ^= 1u;        // the strip is clean: zeroed at start / drained + re-zeroed by the epilogue
+      for (int bt = 0; bt < nbatch; ++bt) {
+        const int s0 = bt * SB, n_in = min(SB, nslices - s0);
         mbar_wait(&full_bar[slot], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // columns of output slices s (kz=0), s-1 (kz=1), s-2 (kz=2) are adjacent
-        const uint32_t d_tmem = tmem_base + (uint32_t)((a.zcap + 1 - s) * CP);
-        const uint32_t sb16 = (rbase + (uint32_t)slot * slot_bytes) >> 4;
+        const uint32_t slot16 = (rbase + (uint32_t)slot * slot_bytes) >> 4;
         if (elect_one()) {
-          uint32_t blo = wb16 | b_lbo;
-          if (a.cin8) {
+          for (int i = 0; i < n_in; ++i) {
+            const int s = s0 + i;
+            // columns of output slices s (kz=0), s-1 (kz=1), s-2 (kz=2) are adjacent
+            const uint32_t d_tmem = tmem_base + (uint32_t)((a.zcap + 1 - s) * CP);
+            const uint32_t sb16 = slot16 + (uint32_t)i * (slice_bytes >> 4);
+            uint32_t blo = wb16 | b_lbo;
+            if (a.dbg & 16) {
+            } else if (a.cin8) {
 #pragma unroll
-            for (int p = 0; p < 5; ++p) {
-              const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
-              const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3));
-              const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3));
-              const uint32_t alo = (sb16 + o0) | ((o1 - o0) << 16);       // LBO = distance between the two taps (0: dummy half)
-              umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
-              blo += (uint32_t)(NP * 32) >> 4;
-            }
-          } else {
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              uint32_t alo = (sb16 + (uint32_t)((t / 3) * HX + (t % 3))) | a_lbo_planes;
-              for (int kc = 0; kc < kcs; ++kc) {
+              for (int p = 0; p < 5; ++p) {
+                const int t0 = 2 * p, t1 = (2 * p + 1 < 9) ? 2 * p + 1 : 2 * p;
+                const uint32_t o0 = (uint32_t)((t0 / 3) * HX + (t0 % 3));
+                const uint32_t o1 = (uint32_t)((t1 / 3) * HX + (t1 % 3));
+                const uint32_t alo = (sb16 + o0) | ((o1 - o0) << 16);       // LBO = distance between the two taps (0: dummy half)
                 umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
-                alo += (uint32_t)(2 * PLANE_STRIDE) >> 4;
                 blo += (uint32_t)(NP * 32) >> 4;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                uint32_t alo = (sb16 + (uint32_t)((t / 3) * HX + (t % 3))) | a_lbo_planes;
+                for (int kc = 0; kc < kcs; ++kc) {
+                  umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
+                  alo += (uint32_t)(2 * PLANE_STRIDE) >> 4;
+                  blo += (uint32_t)(NP * 32) >> 4;
+                }
               }
             }
           }
-          umma_commit(&empty_bar[slot]);                       // the input slice is consumed by this batch only
-          if (s >= 2) umma_commit(&tfull_bar[s - 2]);          // output slice s-2 has received its three kz parts
+          umma_commit(&empty_bar[slot]);                       // the input slices of this step are consumed by it only
+          umma_commit(&tfull_bar[bt]);                         // output slices <= s0 + n_in - 3 have received their three kz parts
         }
         __syncwarp();
         if (++slot == RING3) { slot = 0; ph ^= 1u; }
@@ -165,88 +193,114 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;
-    const int oy = y0 + yl, ox = x0 + xl;
-    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int ew = (warp - 2) >> 2;                 // 0 / 1: this warp drains the even / odd output slices of its quadrant
     if (ew == 0) {
-      // zero the accumulator strip (this quadrant's 32 lanes, all allocated columns)
+      // zero the accumulator strip once (this quadrant's 32 lanes, all allocated columns); afterwards every drained column
+      // group is re-zeroed right after it has been read
       for (int c = 0; c < a.tmem_cols; c += 8) tmem_st8_zero(lane_base + (uint32_t)c);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tzero_bar);
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (lane == 0) mbar_arrive(&strip_bar);
     const bool has_c8[4] = {0 < a.Cout, 8 < a.Cout, 16 < a.Cout, 24 < a.Cout};
     // Operands of the fused epilogue (stored activation of the LeakyReLU' factor) are fetched PF output slices ahead of
     // their use: with one 16 B load per thread and slice in flight an SM keeps only ~4 KB of this stream outstanding,
     // far below what the ~2 us round trip needs (Little's law); PF slices ahead restore the bandwidth.
     constexpr int PF = 32 / CP >= 2 ? 32 / CP * 2 : 2;      // CP = 8: 8 slices, 16: 4, 32: 2  (32 registers)
-    uint4 refq[PF][CP / 8];
     const long long ref_zstride = (long long)a.RY * a.RX * a.ref_C;
-    const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
-    auto fetch_ref = [&](int zo, uint4* q) {
-      if (a.ref && inside && zo < nz) {
+    uint64_t tf_ph = 0;                                      // phase bit of every tfull barrier (an item may use fewer steps)
+    for (int it = blockIdx.x; it < a.items; it += gridDim.x) {
+      int b, x0, y0, z0, nz; decode(it, b, x0, y0, z0, nz);
+      const int nbatch = (nz + 2 + SB - 1) / SB;
+      const int oy = y0 + yl, ox = x0 + xl;
+      const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
+      uint4 refq[PF][CP / 8];
+      const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+      auto fetch_ref = [&](int zo, uint4* qv) {
+        if (a.ref && inside && zo < nz) {
 #pragma unroll
-        for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) q[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ref_base + (long long)zo * ref_zstride + c * 8));
+          for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) qv[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ref_base + (long long)zo * ref_zstride + c * 8));
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < PF; ++u) fetch_ref(2 * u + ew, refq[u]);
+      for (int zb = 0; zb < nz; zb += 2 * PF) {
+#pragma unroll
+        for (int pu = 0; pu < PF; ++pu) {
+          const int zo = zb + 2 * pu + ew;
+          if (zo >= nz) break;
+          const int oz = z0 + zo;
+          // output slice zo has its three kz parts once input slice zo + 2 has been multiplied.  CP == 8: the MMA of input
+          // slice zo + 3 still touches this column group (the fourth, zero-weight group of N = 32 adds 0 to it) and would
+          // write a stale value back over the re-zeroed columns, so that step must have retired as well
+          const int tb = min(zo + (CP == 8 ? 3 : 2), nz + 1) / SB;
+          mbar_wait(&tfull_bar[tb], (uint32_t)(tf_ph >> tb) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t r[CP];
+          const uint32_t taddr = lane_base + (uint32_t)((a.zcap + 1 - zo) * CP);
+#pragma unroll
+          for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + c, r + c);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < CP; c += 8) tmem_st8_zero(taddr + c);          // clean for the next item of this CTA
+          if (!inside) continue;
+          float v[CP];
+#pragma unroll
+          for (int c = 0; c < CP; ++c) v[c] = __uint_as_float(r[c]);
+          if (a.ref) {
+#pragma unroll
+            for (int c = 0; c < CP; c += 8) {
+              if (c < a.Cout) {
+                float f[8];
+                unpack8(refq[pu][c / 8], f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
+              }
+            }
+          }
+          fetch_ref(zo + 2 * PF, refq[pu]);
+          if (a.drop_key) {
+            const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
+          }
+          bf16* op = a.out + ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
+#pragma unroll
+          for (int c = 0; c < CP; c += 8) {
+            if (c < a.Cout) {
+              float o[8];
+              if (a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
+              else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = 0.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                o[u] += v[c + u];
+                if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
+              }
+              uint4 pk;
+              pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(op + c) = pk;
+            }
+          }
+        }
       }
-    };
-#pragma unroll
-    for (int u = 0; u < PF; ++u) fetch_ref(2 * u + ew, refq[u]);
-    for (int zb = 0; zb < nz; zb += 2 * PF) {
-#pragma unroll
-    for (int pu = 0; pu < PF; ++pu) {
-      const int zo = zb + 2 * pu + ew;
-      if (zo >= nz) break;
-      const int oz = z0 + zo;
-      mbar_wait(&tfull_bar[zo], 0);
+      // end of the item: all its MMAs have retired once the last step's barrier has flipped.  The column groups of the
+      // virtual output slices -2, -1 (kz = 1, 2 parts of the first two input slices) and nz, nz + 1 (kz = 0, 1 parts of the
+      // last two) hold partial sums nobody reads: the even / odd warps wipe them
+      mbar_wait(&tfull_bar[nbatch - 1], (uint32_t)(tf_ph >> (nbatch - 1)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r[CP];
-      const uint32_t taddr = lane_base + (uint32_t)((a.zcap + 1 - zo) * CP);
+      {
+        const uint32_t junk = lane_base + (uint32_t)((ew == 0 ? a.zcap + 2 : a.zcap - nz) * CP);
 #pragma unroll
-      for (int c = 0; c < CP; c += 8) tmem_ld8(taddr + c, r + c);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!inside) continue;
-      float v[CP];
-#pragma unroll
-      for (int c = 0; c < CP; ++c) v[c] = __uint_as_float(r[c]);
-      if (a.ref) {
-#pragma unroll
-        for (int c = 0; c < CP; c += 8) {
-          if (c < a.Cout) {
-            float f[8];
-            unpack8(refq[pu][c / 8], f);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
-          }
-        }
+        for (int c = 0; c < 2 * CP; c += 8) tmem_st8_zero(junk + c);
       }
-      fetch_ref(zo + 2 * PF, refq[pu]);
-      if (a.drop_key) {
-        const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
-      }
-      bf16* op = a.out + ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
-#pragma unroll
-      for (int c = 0; c < CP; c += 8) {
-        if (c < a.Cout) {
-          float o[8];
-          if (a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
-          else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) o[u] = 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            o[u] += v[c + u];
-            if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
-          }
-          uint4 pk;
-          pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(op + c) = pk;
-        }
-      }
-    }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(&strip_bar);
+      tf_ph ^= (nbatch >= 64) ? ~0ull : ((1ull << nbatch) - 1ull);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,6 +341,7 @@ __global__ void pack_weights3_kernel(const Pack3Args a) {
   a.dst[i] = __float2bfloat16_rn(v);
 }
 
+int sb_of(int spd) { const int sb = 30 / spd; return sb < 1 ? 1 : (sb > 8 ? 8 : sb); }   // input slices per pipeline step
 int cp_of(int cout) { return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32); }
 int np_of(int cp) { return cp == 8 ? 32 : 3 * cp; }
 
@@ -304,7 +359,7 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (a.C1 && (a.s1.dtype != DT_BF16 || a.s1.C % 8 || a.s1.coff != 0 || a.s1.C != a.C1)) return false;
   if (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8) return false;
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
-  const size_t smem = ((tc3_packed_bytes(cin, a.Cout) + 1023) & ~(size_t)1023) + (size_t)4 * (cin / 8) * PLANE_STRIDE + 1024;
+  const size_t smem = ((tc3_packed_bytes(cin, a.Cout) + 1023) & ~(size_t)1023) + (size_t)2 * sb_of(cin == 8 ? 5 : 9 * (cin / 16)) * (cin / 8) * PLANE_STRIDE + 1024;   // two pipeline steps at least
   if (smem > 200 * 1024) return false;
   if (a.conv_off[0] || a.conv_off[1] || a.conv_off[2]) return false;
   return tem_get_encode() != nullptr;
@@ -361,14 +416,25 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
   if (a.C1) { if (!tem_make_map_plane(&m1, &t.merged1, a.s1.p, a.B, a.s1.Z, a.s1.Y, a.s1.X, a.s1.C, HX, HY)) return cudaErrorInvalidValue; }
   else { m1 = m0; t.merged1 = t.merged0; }
-  // bytes in flight hide the ~2 us TMA round trip (Little's law): ring as deep as ~48 KB per CTA allow
+  // pipeline step = sb input slices with >= ~24 MMAs between two barrier round trips (see the kernel); the ring holds
+  // ~56 KB per CTA in flight (Little's law at the ~2 us TMA round trip), at least two steps
+  static const char* sb_s = getenv("TEM_TC3_SB");
+  int sb = sb_s ? atoi(sb_s) : sb_of(t.spd);
+  if (sb < 1) sb = 1; if (sb > 8) sb = 8;
+  if (sb > t.zc + 2) sb = t.zc + 2;
+  t.sb = sb;
+  const size_t step_bytes = (size_t)sb * (cin / 8) * PLANE_STRIDE;
   static const char* ring_s = getenv("TEM_TC3_RING");
-  int ring = ring_s ? atoi(ring_s) : (int)((48 * 1024) / ((size_t)(cin / 8) * PLANE_STRIDE));
+  int ring = ring_s ? atoi(ring_s) : (int)((56 * 1024) / step_bytes);
   if (ring > RING3_MAX) ring = RING3_MAX;
-  if (ring < 4) ring = 4;
+  if (ring < 2) ring = 2;
   t.ring = ring;
-  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)ring * (cin / 8) * PLANE_STRIDE + 1024;
-  const unsigned grid = (unsigned)(cols * t.nzc);
+  const size_t smem = (((size_t)t.wbytes + 1023) & ~(size_t)1023) + (size_t)ring * step_bytes + 1024;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  t.items = (int)(cols * t.nzc);
+  t.nbmax = (t.zc + 2 + sb - 1) / sb;
+  if (t.nbmax > kMaxChunk) return cudaErrorInvalidConfiguration;
+  const unsigned grid = (unsigned)(t.items < 2 * 148 ? t.items : 2 * 148);     // persistent: two CTAs per SM
   static bool attr[3] = {false, false, false};
 #define LAUNCH_TC3(CPV, IDX)                                                                                            \
   {                                                                                                                     \

@@ -166,6 +166,21 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& a, cudaStream_t st);
 bool wgrad_c1_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_c1(const WgradArgs& a, cudaStream_t st);
 
+// disc_tail.cu: fused tail of the 3-D discriminator (d5 .. d8: 64 -> 1 voxels per sample), one CTA per sample
+struct DiscTailArgs {
+  int B, C4, e4, e5;                       // a4: [B, e4^3, C4];  a5: [B, e5^3, 32], e5 = e4 - 2 in {4, 5}
+  const bf16* a4; bf16 *a5, *a6, *a7;      // stored activations (forward writes a5..a7, backward reads a4..a7)
+  float* logits;                           // [B] fp32
+  const float *w5, *w6, *w7, *w8, *b8;     // fp32 master weights, Keras layouts
+  float slope4, slope5, slope6, slope7;    // LeakyReLU slopes of d4 .. d7 (d6: 0.3^2, discriminator.py:73-74)
+  const float* dlogits;                    // backward: [B] fp32
+  bf16* d_a4;                              // backward: gradient w.r.t. a4, LeakyReLU'(a4) applied
+  float *dw5, *dw6, *dw7, *dw8, *db8;      // backward: weight-gradient accumulators (nullptr: data gradient only)
+};
+bool disc_tail_supported(const DiscTailArgs& a);
+cudaError_t launch_disc_tail_fwd(const DiscTailArgs& a, cudaStream_t st);
+cudaError_t launch_disc_tail_bwd(const DiscTailArgs& a, cudaStream_t st);
+
 // elementwise.cu
 cudaError_t launch_focal_logits(const float* x, long long n, float target, float gamma, float scale, int mode,
                                 float* loss_out, float* grad, cudaStream_t st);

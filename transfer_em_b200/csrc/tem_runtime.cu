@@ -456,6 +456,29 @@ static int gen_backward(tem_handle* h, int net, GenPass& P, float* dout, float* 
 // ------------------------------------------------------------------------------------------
 // discriminator passes
 // ------------------------------------------------------------------------------------------
+// fused d5..d8 tail (disc_tail.cu): 3-D models whose d6 output is one voxel per sample, wf >= 4
+static bool disc_tail_args(const tem_handle* h, const NetSpec& N, const float* w, float* g, DiscPass& P, const int d[9], int B, DiscTailArgs& t) {
+  static const bool off = getenv("TEM_NO_DISC_TAIL") != nullptr;      // debug knob: layer-by-layer path
+  memset(&t, 0, sizeof(t));
+  if (off || h->nd != 3 || !h->cfg.use_tensor_cores || d[6] != 1 || d[7] != 1 || d[8] != 1) return false;
+  if (N.L[5].cout != 32 || N.L[6].cin != 32 || N.L[6].cout != 32 || N.L[7].cin != 32) return false;
+  t.B = B; t.C4 = N.L[4].cout; t.e4 = d[4]; t.e5 = d[5];
+  t.a4 = (const bf16*)P.a[4].p; t.a5 = (bf16*)P.a[5].p; t.a6 = (bf16*)P.a[6].p; t.a7 = (bf16*)P.a[7].p; t.logits = (float*)P.a[8].p;
+  t.w5 = w + N.L[5].w_off; t.w6 = w + N.L[6].w_off; t.w7 = w + N.L[7].w_off; t.w8 = w + N.L[8].w_off; t.b8 = w + N.L[8].b_off;
+  t.slope4 = N.L[4].slope; t.slope5 = N.L[5].slope; t.slope6 = N.L[6].slope; t.slope7 = N.L[7].slope;
+  if (g) { t.dw5 = g + N.L[5].w_off; t.dw6 = g + N.L[6].w_off; t.dw7 = g + N.L[7].w_off; t.dw8 = g + N.L[8].w_off; t.db8 = g + N.L[8].b_off; }
+  return disc_tail_supported(t);
+}
+static double tail_flops(const DiscTailArgs& t) {
+  const double v5 = (double)t.e5 * t.e5 * t.e5;
+  return 2.0 * t.B * (v5 * 27 * t.C4 * 32 + 64.0 * 32 * 32 + 32.0 * t.C4 + t.C4);
+}
+static double tail_bytes(const NetSpec& N, const DiscTailArgs& t, bool bwd) {
+  const double v4 = (double)t.e4 * t.e4 * t.e4, v5 = (double)t.e5 * t.e5 * t.e5;
+  const double wts = 4.0 * (N.L[5].w_count + N.L[6].w_count + N.L[7].w_count + N.L[8].w_count);
+  return t.B * (v4 * t.C4 + v5 * 32 + 32 + t.C4) * 2.0 * (bwd ? 2 : 1) + wts * (bwd && t.dw5 ? 2 : 1);
+}
+
 static int disc_forward(tem_handle* h, int net, DiscPass& P, const InputRef& in, int B, int m, cudaStream_t st) {
   const NetSpec& N = h->nets[net];
   const float* w = h->params + N.arena_off;
@@ -466,8 +489,15 @@ static int disc_forward(tem_handle* h, int net, DiscPass& P, const InputRef& in,
   const int f = disc_first(h->nd);
   SrcView vin = view_of_input(in);
   TEM_CHECK(run_forward(h, N.L[f], w, vin, 1, nullptr, 0, P.a[f], B, 0, in.use_lut, in.mean, in.stdv, st));
-  for (int i = f + 1; i < 9; ++i)
+  DiscTailArgs ta;
+  const bool fused = disc_tail_args(h, N, w, nullptr, P, d, B, ta);
+  for (int i = f + 1; i < (fused ? 5 : 9); ++i)
     TEM_CHECK(run_forward(h, N.L[i], w, view_of(P.a[i - 1]), N.L[i].cin, nullptr, 0, P.a[i], B, 0, 0, 0, 0, st));
+  if (fused) {
+    ProfScope ps(h, "dtail", "fwd", tail_bytes(N, ta, false), tail_flops(ta), st);
+    g_tem_last_kernel = "disc_tail_fwd_kernel";
+    TEM_CUDA(launch_disc_tail_fwd(ta, st));
+  }
   return TEM_OK;
 }
 
@@ -481,7 +511,18 @@ static int disc_backward(tem_handle* h, int net, DiscPass& P, float* dlogits, bo
   for (int i = 0; i < 8; ++i) { dP[i] = h->ddP[set][i]; spatial(h, d[i] > 0 ? d[i] : 1, dP[i].d); }
   dP[8] = P.a[8]; dP[8].p = dlogits;
   const int f = disc_first(h->nd);
-  for (int li = 8; li > f; --li) {
+  int top = 8;
+  DiscTailArgs ta;
+  if (disc_tail_args(h, N, w, do_wgrad ? g : nullptr, P, d, B, ta)) {
+    ta.dlogits = dlogits; ta.d_a4 = (bf16*)dP[4].p;
+    if (disc_tail_supported(ta)) {
+      ProfScope ps(h, "dtail", do_wgrad ? "bwd" : "dgrad", tail_bytes(N, ta, true), tail_flops(ta) * (do_wgrad ? 2 : 1), st);
+      g_tem_last_kernel = "disc_tail_bwd_kernel";
+      TEM_CUDA(launch_disc_tail_bwd(ta, st));
+      top = 4;
+    }
+  }
+  for (int li = top; li > f; --li) {
     const LayerSpec& L = N.L[li];
     if (do_wgrad) {
       TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[li - 1]), 0, L.cin, dP[li], B, 0, 0, 0, st));

@@ -29,7 +29,7 @@ extern unsigned long long g_tem_launches;
 
 namespace {
 
-constexpr int XR_MAX = 8, DR_MAX = 10;       // ring depths (x slices, g slices) are chosen per launch
+constexpr int XR_MAX = 8;                    // pipeline slots (chosen per launch)
 constexpr int kThreads = 192;
 
 struct WtArgs {
@@ -42,10 +42,12 @@ struct WtArgs {
   int shift[3];                // x tensor coordinate = x-window coordinate + shift
   int nrg, nzc, zc;            // row groups, z chunks, x slices per chunk
   int units;                   // work units (sample, row group, z chunk); CTAs are persistent over them
-  int XR, DR;                  // ring depths
+  int XR, sb;                  // pipeline slots, x slices per pipeline step
   int tmem_cols;
   int xa_bytes, gb_bytes;      // bytes of one ring slot
   float* dw; long long ws_tap, ws_a, ws_b;
+  int vec4;                    // dw rows are contiguous in cb and 16 B aligned: red.global.add.v4.f32
+  int dbg;                     // stage-ablation bits (-DTEM_ABLATION builds only): 1 no epilogue, 2 no atomics, 4 no x loads, 8 no g loads, 16 no MMAs
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -57,12 +59,17 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const WtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t xfull[XR_MAX], xempty[XR_MAX], gfull[DR_MAX], gempty[DR_MAX], done_bar;
-  const int XR = a.XR, DR = a.DR;
+  __shared__ uint64_t full[XR_MAX], empty[XR_MAX], done_bar;
+  const int NSLOT = a.XR, SB = a.sb;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* xring = smem;
-  uint8_t* gring = smem + (size_t)a.XR * a.xa_bytes;
+  // One pipeline step = SB consecutive x z-slices of a work unit plus the SB + 2 g slices they correlate with (the two
+  // g slices shared with the next step are simply loaded again: they come from L2).  Measured (tools/ubench/sync_latency.cu):
+  // a full / empty hand-over costs the issuing warp ~300-400 cycles whatever the ring depth, the 18 MMAs of one g7 slice
+  // ~500: with one hand-over per slice the issue loop bounded the small layers (stage ablation: 23 of 31 us remained on g7
+  // with loads and MMAs switched off).  Layout of a slot: [SB x-slices][SB + 2 g-slices].
+  const uint32_t slot_bytes = (uint32_t)(SB * a.xa_bytes + (SB + 2) * a.gb_bytes);
+  const uint32_t g_off = (uint32_t)(SB * a.xa_bytes);
 
   // work unit u -> (sample b, first g row y0, first x slice zx0, slices nzx)
   auto decode = [&](int u, int& b, int& y0, int& zx0, int& nzx) {
@@ -73,8 +80,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < XR; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < DR; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -89,29 +95,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      int gslot = 0; uint32_t gph = 0; int xslot = 0; uint32_t xph = 0;
+      int slot = 0; uint32_t ph = 0;
+      const int xplane = a.RA * a.WA * 16, gplane = a.RB * a.WB * 16;
       for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
         int b, y0, zx0, nzx; decode(u, b, y0, zx0, nzx);
-        // g slices zx0-2 .. zx0+nzx-1 (index i = zd - (zx0-2)); x slices zx0 .. zx0+nzx-1 (step s)
-        auto load_g = [&](int i) {
-          mbar_wait(&gempty[gslot], gph ^ 1u);
-          mbar_arrive_expect_tx(&gfull[gslot], (uint32_t)a.gb_bytes);
-          uint8_t* dst = gring + (size_t)gslot * a.gb_bytes;
-          const int plane_bytes = a.RB * a.WB * 16;
-          for (int p = 0; p < a.pb; ++p)
-            tma_load_5d(dst + p * plane_bytes, &mapg, &gfull[gslot], p * 8, -2, y0, zx0 - 2 + i, b);
-          if (++gslot == DR) { gslot = 0; gph ^= 1u; }
-        };
-        load_g(0); load_g(1);
-        for (int s = 0; s < nzx; ++s) {
-          load_g(s + 2);
-          mbar_wait(&xempty[xslot], xph ^ 1u);
-          mbar_arrive_expect_tx(&xfull[xslot], (uint32_t)a.xa_bytes);
-          uint8_t* dst = xring + (size_t)xslot * a.xa_bytes;
-          const int plane_bytes = a.RA * a.WA * 16;
-          for (int p = 0; p < a.pa; ++p)
-            tma_load_5d(dst + p * plane_bytes, &mapx, &xfull[xslot], p * 8, a.shift[2], y0 + a.shift[1], zx0 + s + a.shift[0], b);
-          if (++xslot == XR) { xslot = 0; xph ^= 1u; }
+        for (int s0 = 0; s0 < nzx; s0 += SB) {
+          const int n = min(SB, nzx - s0);
+          mbar_wait(&empty[slot], ph ^ 1u);
+          uint8_t* base = smem + (size_t)slot * slot_bytes;
+          const int ng = (a.dbg & 8) ? 0 : n + 2, nx = (a.dbg & 4) ? 0 : n;
+          if (ng + nx == 0) mbar_arrive(&full[slot]);
+          else mbar_arrive_expect_tx(&full[slot], (uint32_t)(nx * a.xa_bytes + ng * a.gb_bytes));
+          // g slice i of the step is z = zx0 + s0 + i - 2 (OOB rows / slices are zero filled: the padding of g)
+          for (int i = 0; i < ng; ++i)
+            for (int p = 0; p < a.pb; ++p)
+              tma_load_5d(base + g_off + i * a.gb_bytes + p * gplane, &mapg, &full[slot], p * 8, -2, y0, zx0 + s0 + i - 2, b);
+          for (int i = 0; i < nx; ++i)
+            for (int p = 0; p < a.pa; ++p)
+              tma_load_5d(base + i * a.xa_bytes + p * xplane, &mapx, &full[slot], p * 8, a.shift[2], y0 + a.shift[1], zx0 + s0 + i + a.shift[0], b);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
       }
     }
@@ -124,65 +126,62 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
       // the single issuing thread spends a couple of integer adds per MMA instead of rebuilding 64-bit descriptors
       const uint32_t lo_fixed = (128u >> 4) << 16;                                   // LBO = 128 B (next 8 voxels)
       const uint32_t a_hi = (((uint32_t)a.WA * 16u) >> 4) | (1u << 14), b_hi = (((uint32_t)a.WB * 16u) >> 4) | (1u << 14);   // SBO, version
-      const uint32_t xbase16 = smem_u32(xring) >> 4, gbase16 = smem_u32(gring) >> 4;
-      const uint32_t xa16 = (uint32_t)a.xa_bytes >> 4, gb16 = (uint32_t)a.gb_bytes >> 4;
+      const uint32_t sbase16 = smem_u32(smem) >> 4;
+      const uint32_t xa16 = (uint32_t)a.xa_bytes >> 4, gb16 = (uint32_t)a.gb_bytes >> 4, slot16 = slot_bytes >> 4, goff16 = g_off >> 4;
       const uint32_t N = (uint32_t)a.N;
-      int gwslot = 0; uint32_t gwph = 0;                    // next g slot to wait for
-      int xslot = 0; uint32_t xph = 0;
-      int gold = 0;                                         // ring slot of the oldest live g slice
+      int slot = 0; uint32_t ph = 0;
       uint32_t acc = 0u;
-      auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t accf) {
-        if (!elect_one()) return;
-        uint64_t ad, bd;
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(ad) : "r"(alo), "r"(a_hi));
-        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(bd) : "r"(blo), "r"(b_hi));
-        umma_bf16(d, ad, bd, idesc, accf);
-      };
       for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
         int b, y0, zx0, nzx; decode(u, b, y0, zx0, nzx);
-        // the first two g slices of the unit
-        for (int i = 0; i < 2; ++i) { mbar_wait(&gfull[gwslot], gwph); if (++gwslot == DR) { gwslot = 0; gwph ^= 1u; } }
-        for (int s = 0; s < nzx; ++s) {
-          mbar_wait(&gfull[gwslot], gwph); if (++gwslot == DR) { gwslot = 0; gwph ^= 1u; }
-          mbar_wait(&xfull[xslot], xph);
+        for (int s0 = 0; s0 < nzx; s0 += SB) {
+          const int n = min(SB, nzx - s0);
+          mbar_wait(&full[slot], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          int g1s = gold + 1; if (g1s >= DR) g1s -= DR;
-          int g2s = gold + 2; if (g2s >= DR) g2s -= DR;
-          // dz = 0, 1, 2 read g index s+2, s+1, s  (zd = zx - dz); +2 voxels: the g tile starts at x = -2
-          const uint32_t b0 = (gbase16 + (uint32_t)g2s * gb16 + 2u) | lo_fixed;
-          const uint32_t b1 = (gbase16 + (uint32_t)g1s * gb16 + 2u) | lo_fixed;
-          const uint32_t b2 = (gbase16 + (uint32_t)gold * gb16 + 2u) | lo_fixed;
-          uint32_t alo = (xbase16 + (uint32_t)xslot * xa16) | lo_fixed;
-          for (int r = 0; r < a.NR; ++r) {
-            const uint32_t ro = (uint32_t)r * 16u;           // 16 voxels = 256 B = 16 descriptor units
-            mma(tmem_base + 0 * N, alo, b0 + ro, acc);      mma(tmem_base + 1 * N, alo, b0 + ro - 1u, acc); mma(tmem_base + 2 * N, alo, b0 + ro - 2u, acc);
-            mma(tmem_base + 3 * N, alo, b1 + ro, acc);      mma(tmem_base + 4 * N, alo, b1 + ro - 1u, acc); mma(tmem_base + 5 * N, alo, b1 + ro - 2u, acc);
-            mma(tmem_base + 6 * N, alo, b2 + ro, acc);      mma(tmem_base + 7 * N, alo, b2 + ro - 1u, acc); mma(tmem_base + 8 * N, alo, b2 + ro - 2u, acc);
-            alo += 16u; acc = 1u;
-          }
           if (elect_one()) {
-            umma_commit(&xempty[xslot]);
-            umma_commit(&gempty[gold]);                      // g index s (zd = zx - 2) is not needed by later x slices
-            if (s == nzx - 1) { umma_commit(&gempty[g1s]); umma_commit(&gempty[g2s]); }   // end of the unit: the last two g slices too
+            const uint32_t xb = sbase16 + (uint32_t)slot * slot16, gb = xb + goff16 + 2u;     // +2 voxels: the g tile starts at x = -2
+            if (!(a.dbg & 16)) {
+              for (int i = 0; i < n; ++i) {
+                // dz = 0, 1, 2 read g slice i+2, i+1, i of the step (zd = zx - dz)
+                const uint32_t b0 = (gb + (uint32_t)(i + 2) * gb16) | lo_fixed;
+                const uint32_t b1 = (gb + (uint32_t)(i + 1) * gb16) | lo_fixed;
+                const uint32_t b2 = (gb + (uint32_t)i * gb16) | lo_fixed;
+                uint32_t alo = (xb + (uint32_t)i * xa16) | lo_fixed;
+                for (int r = 0; r < a.NR; ++r) {
+                  const uint32_t ro = (uint32_t)r * 16u;           // 16 voxels = 256 B = 16 descriptor units
+                  const uint64_t ad = ((uint64_t)a_hi << 32) | alo;
+#define WT_MMA(ACC, BLO) umma_bf16(tmem_base + (ACC) * N, ad, ((uint64_t)b_hi << 32) | (BLO), idesc, acc)
+                  WT_MMA(0, b0 + ro); WT_MMA(1, b0 + ro - 1u); WT_MMA(2, b0 + ro - 2u);
+                  WT_MMA(3, b1 + ro); WT_MMA(4, b1 + ro - 1u); WT_MMA(5, b1 + ro - 2u);
+                  WT_MMA(6, b2 + ro); WT_MMA(7, b2 + ro - 1u); WT_MMA(8, b2 + ro - 2u);
+#undef WT_MMA
+                  alo += 16u; acc = 1u;
+                }
+              }
+            }
+            umma_commit(&empty[slot]);
           }
           __syncwarp();
-          if (++xslot == XR) { xslot = 0; xph ^= 1u; }
-          if (++gold == DR) gold = 0;
+          acc = 1u;
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
-        gold += 2; if (gold >= DR) gold -= DR;               // the next unit starts with fresh g slices
       }
       if (elect_one()) umma_commit(&done_bar);
       __syncwarp();
     }
   }
-  // ---- epilogue: fold the useful diagonals of the 9 accumulators into a shared dw image, then one atomic per weight
+  // ---- epilogue: fold the useful diagonals of the 9 accumulators into a shared dw image, then one vector reduction per
+  // four weights and CTA.  The image rows ([tap][ca] x Cb floats) are padded by 4 floats: the eight lanes of a quarter
+  // warp hold eight consecutive ca, i.e. rows 144 B apart (Cb = 32), and their float4 read-modify-writes fall into
+  // eight different 16 B bank groups (unpadded: all into the same one, 1.8 M conflicts on g7 in the round-1 capture).
   float* red = reinterpret_cast<float*>(smem);
   const int Ca = a.pa * 8, Cb = a.pb * 8;
-  const int nred = 27 * Ca * Cb;
-  if (warp >= 2) {
+  const int CbP = Cb + 4;
+  const int nrow = 27 * Ca;
+  if (warp >= 2 && !(a.dbg & 1)) {
     mbar_wait(&done_bar, 0);                                 // all MMAs retired: rings are free, accumulators final
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int i = threadIdx.x - 64; i < nred; i += 128) red[i] = 0.f;
+    const int tid = threadIdx.x - 64;
+    for (int i = tid; i < nrow * CbP / 4; i += 128) reinterpret_cast<float4*>(red)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int q = warp & 3;
     // M = 128: TMEM lane = row.  M = 64: rows 16q .. 16q+15 live in lanes 0..15 of subpartition q.
@@ -190,7 +189,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
     const bool rowok = (a.M == 128) || lane < 16;
     const int gm = m >> 3, pA = gm / a.RA, gi = gm % a.RA, ca = pA * 8 + (m & 7);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int ngn = a.N >> 3;
     // Round j folds the column groups of g row j: in one round an address (tap, ca, cb) is touched by exactly one
     // thread (x row i <-> dy = i - j), so plain read-modify-writes suffice; rounds are separated by a named barrier.
     for (int j = 0; j < a.RB; ++j) {
@@ -198,29 +196,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
       const bool use = rowok && ty >= 0 && ty < 3;
       for (int acc = 0; acc < 9; ++acc) {
         const int dz = acc / 3, dx = acc % 3;
-        for (int pB = 0; pB < a.pb; ++pB) {
-          uint32_t r[8];
+        float* rowp = red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * CbP;
+        for (int pB = 0; pB < a.pb; pB += 2) {              // two 8-column loads in flight per wait
+          uint32_t r[16];
           tmem_ld8(lane_base + (uint32_t)(acc * a.N + (pB * a.RB + j) * 8), r);
+          if (pB + 1 < a.pb) tmem_ld8(lane_base + (uint32_t)(acc * a.N + ((pB + 1) * a.RB + j) * 8), r + 8);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (use) {
-            float4* dst = reinterpret_cast<float4*>(red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * Cb + pB * 8);
-            float4 v0 = dst[0], v1 = dst[1];
-            v0.x += __uint_as_float(r[0]); v0.y += __uint_as_float(r[1]); v0.z += __uint_as_float(r[2]); v0.w += __uint_as_float(r[3]);
-            v1.x += __uint_as_float(r[4]); v1.y += __uint_as_float(r[5]); v1.z += __uint_as_float(r[6]); v1.w += __uint_as_float(r[7]);
-            dst[0] = v0; dst[1] = v1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (pB + h < a.pb) {
+                float4* dst = reinterpret_cast<float4*>(rowp + (pB + h) * 8);
+                float4 v0 = dst[0], v1 = dst[1];
+                v0.x += __uint_as_float(r[8 * h + 0]); v0.y += __uint_as_float(r[8 * h + 1]); v0.z += __uint_as_float(r[8 * h + 2]); v0.w += __uint_as_float(r[8 * h + 3]);
+                v1.x += __uint_as_float(r[8 * h + 4]); v1.y += __uint_as_float(r[8 * h + 5]); v1.z += __uint_as_float(r[8 * h + 6]); v1.w += __uint_as_float(r[8 * h + 7]);
+                dst[0] = v0; dst[1] = v1;
+              }
+            }
           }
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // every CTA starts its pass over the dw image at a different offset: fewer same-address collisions in L2
-    const int rot = (int)(((long long)blockIdx.x * nred / gridDim.x) & ~127LL);
-    for (int i0 = threadIdx.x - 64; i0 < nred; i0 += 128) {
-      int i = i0 + rot; if (i >= nred) i -= nred;
-      const float v = red[i];
-      if (v != 0.f) {
-        const int cb = i % Cb, t = i / Cb, cA = t % Ca, tap = t / Ca;
-        atomicAdd(a.dw + (long long)tap * a.ws_tap + (long long)cA * a.ws_a + (long long)cb * a.ws_b, v);
+    // every CTA starts its pass over the dw image at a different offset (fewer same-address collisions in L2); Ca and Cb
+    // are powers of two (8 / 16 / 32): shifts instead of divisions
+    const int lg_cb4 = (Cb == 8) ? 1 : (Cb == 16 ? 2 : 3), lg_ca = (Ca == 8) ? 3 : (Ca == 16 ? 4 : 5);
+    const int n4 = nrow << lg_cb4;
+    const int rot = (int)(((long long)blockIdx.x * n4 / gridDim.x) & ~127LL);
+    if (!(a.dbg & 2)) {
+      for (int i0 = tid; i0 < n4; i0 += 128) {
+        int i = i0 + rot; if (i >= n4) i -= n4;
+        const int row = i >> lg_cb4, c4 = i & ((1 << lg_cb4) - 1);
+        const float4 v = *reinterpret_cast<const float4*>(red + (size_t)row * CbP + c4 * 4);
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+          const int tap = row >> lg_ca, cA = row & (Ca - 1);
+          float* dst = a.dw + (long long)tap * a.ws_tap + (long long)cA * a.ws_a + (long long)(c4 * 4) * a.ws_b;
+          if (a.vec4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          } else {
+            atomicAdd(dst, v.x); atomicAdd(dst + a.ws_b, v.y); atomicAdd(dst + 2 * a.ws_b, v.z); atomicAdd(dst + 3 * a.ws_b, v.w);
+          }
+        }
       }
     }
   }
@@ -251,13 +267,18 @@ bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
   t.xa_bytes = t.pa * t.RA * t.WA * 16; t.gb_bytes = t.pb * t.RB * t.WB * 16;
   int cols = 32; while (cols < 9 * t.N) cols <<= 1;
   t.tmem_cols = cols;
-  // rings as deep as ~150 KB allow (one CTA per SM anyway: the accumulators take most of TMEM)
-  static const char* ring_s = getenv("TEM_WTC_RING");    // debug knob: cap of the x ring depth
-  const int xr_cap = ring_s ? atoi(ring_s) : XR_MAX;
-  t.XR = 3; t.DR = 5;
-  while (t.XR < xr_cap && t.XR < XR_MAX && (size_t)(t.XR + 1) * t.xa_bytes + (size_t)(t.DR + 1) * t.gb_bytes <= 150 * 1024) { ++t.XR; ++t.DR; }
-  smem = (size_t)t.XR * t.xa_bytes + (size_t)t.DR * t.gb_bytes + 1024;
-  const size_t red = (size_t)27 * w.Ca * w.Cb * 4;
+  // pipeline step: sb x-slices with >= ~64 MMAs between two hand-overs (at least 2: a step re-loads two g slices);
+  // as many slots as ~150 KB allow (one CTA per SM anyway: the accumulators take most of TMEM), at least two
+  static const char* sb_s = getenv("TEM_WTC_SB");        // debug knob
+  int sb = sb_s ? atoi(sb_s) : (64 + 9 * t.NR - 1) / (9 * t.NR);
+  if (sb < 2) sb = 2; if (sb > 6) sb = 6;
+  auto slot_of = [&](int n) { return (size_t)n * t.xa_bytes + (size_t)(n + 2) * t.gb_bytes; };
+  while (sb > 1 && 2 * slot_of(sb) > 180 * 1024) --sb;
+  t.sb = sb;
+  t.XR = 2;
+  while (t.XR < XR_MAX && (size_t)(t.XR + 1) * slot_of(sb) <= 150 * 1024) ++t.XR;
+  smem = (size_t)t.XR * slot_of(sb) + 1024;
+  const size_t red = (size_t)27 * w.Ca * (w.Cb + 4) * 4;
   if (red + 1024 > smem) smem = red + 1024;
   return smem <= 200 * 1024;
 }
@@ -281,7 +302,9 @@ cudaError_t launch_wgrad_tc(const WgradArgs& w, cudaStream_t st) {
   WtArgs t; size_t smem;
   if (!plan(w, t, smem)) return cudaErrorInvalidConfiguration;
   if ((long long)w.B * w.L[0] * w.L[1] * w.L[2] == 0) return cudaSuccess;
+  t.dbg = tem_ablation_bits();
   t.dw = w.dw; t.ws_tap = w.ws_tap; t.ws_a = w.ws_a; t.ws_b = w.ws_b;
+  t.vec4 = w.ws_b == 1 && (reinterpret_cast<uintptr_t>(w.dw) & 15) == 0 && (w.ws_tap & 3) == 0 && (w.ws_a & 3) == 0;
   t.nrg = (w.L[1] + t.RB - 1) / t.RB;
   // z chunks: one CTA per SM (the accumulators take most of TMEM); pick the chunk count with the best wave efficiency
   const long long cols = (long long)w.B * t.nrg;
