@@ -136,10 +136,22 @@ def cpu_train_sample(steps, warmup, B=1):
             "ms_per_step": dt / steps * 1e3, "host_cpus": os.cpu_count()}
 
 
+def host_threads():
+    """All host cores for the CPU arm: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which made the N > 1
+    reference lines of round 1 single-threaded."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    host_threads()
+    if args.config == 5:
+        return run_reference_inference(args, emit)
     # bounded sample: one batch-1 train step per "step" (a batch-8 step takes ~10 s on host cores)
     steps, warmup = args.steps, min(args.warmup, 2)
     res = cpu_train_sample(steps, warmup, B=1)
@@ -148,13 +160,135 @@ def run_reference(args, emit):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("BASELINE config 3" if (WF, DIM) == (8, 74) else "width sweep") +
                                    f": 3D CycleGAN full train step, EM2EM({DIM}, is3d, wf={WF}), focal losses",
-                       "dimsize": DIM, "wf": WF, "per_gpu_batch": args.batch, "global_batch": args.batch, "parallelism": "host threads",
+                       "dimsize": DIM, "wf": WF, "per_gpu_batch": 1, "global_batch": 1, "gpu_arm_per_gpu_batch": args.batch,
+                       "parallelism": f"host threads ({res['cores']})",
                        "sample": "each timed step is ONE batch-1 train step of that workload on the host cores (bounded sample; "
                                  "voxels/s is per-sample throughput, so it compares directly with the batch-8 GPU arm)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: large-subvolume tiled inference (transfer_em/utils.py:41-130), z-slab sharded
+# ------------------------------------------------------------------------------------------------
+def gen_forward_bytes(n, wf):
+    """Algorithmic bytes of ONE generator forward on an n^3 tile: every layer reads its input once and writes
+    its output once, bf16 activations, uint8 source, crop-and-concat skips read as windows, fp32 weights once; the last layer
+    of the fused inference path writes the kept (n - 38)^3 uint8 voxels.  Also returns the FLOPs (2 x MACs)."""
+    c1, c2, c4 = 64 // wf, 128 // wf, 256 // wf
+    d = [n - 2]; d.append(d[0] - 2); d.append((d[1] - 4) // 2 + 1); d.append(d[2] - 2); d.append((d[3] - 4) // 2 + 1); d.append(d[4] - 2)
+    d.append(d[5] * 2); d.append(d[6] - 2); d.append(d[7] - 2); d.append(d[8] * 2); d.append(d[9] - 2); d.append(d[10] - 2)
+    cin = [1, c1, c1, c1, c2, c2, 2 * c2, 2 * c2, c4, 2 * c1, 2 * c1, c2]
+    cout = [c1, c1, c1, c2, c2, 2 * c2, c2, c4, 2 * c1, c1, c2, 1]
+    k = [3, 3, 4, 3, 4, 3, 4, 3, 3, 4, 3, 3]
+    ind = [n] + d[:-1]
+    byt = 0.0; macs = 0.0
+    for i in range(12):
+        in_b = ind[i] ** 3 * cin[i] * (1 if i == 0 else 2)
+        if i in (7, 10):       # cat(up, crop(skip)): both halves are windows of the output extent + 2
+            in_b = (d[i] + 2) ** 3 * cin[i] * 2
+        out_b = d[i] ** 3 * cout[i] * 2 if i < 11 else (n - 38) ** 3
+        byt += in_b + out_b + k[i] ** 3 * cin[i] * cout[i] * 4
+        macs += (ind[i] ** 3 if i in (6, 9) else d[i] ** 3) * cin[i] * cout[i] * k[i] ** 3
+    return byt, 2.0 * macs
+
+
+def cpu_inference_sample(tiles=3):
+    """The reference's per-tile loop (utils.py:107-121) on the host cores: batch-1 generator forward + uint8 conversion."""
+    import torch
+    from oracle import tem_oracle as O
+    rng = np.random.default_rng(7)
+    P = [torch.tensor(p) for p in O.init_params(O.generator_layers(WF), True, rng)]
+    xs = [O.standardize_population(O.scale_tensor(rng.integers(0, 256, (74, 74, 74), dtype=np.uint8)), MEANSTD_X)[None] for _ in range(2)]
+    with torch.no_grad():
+        O.generator_forward(P, torch.tensor(xs[0]), WF, True)
+        t0 = time.perf_counter()
+        for i in range(tiles):
+            y = O.generator_forward(P, torch.tensor(xs[i % 2]), WF, True).numpy()
+            O.to_uint8_reference(y, MEANSTD_Y)[:, 2:-2, 2:-2, 2:-2]
+        dt = time.perf_counter() - t0
+    return {"value": tiles * 36 ** 3 / dt / 1e6, "unit": "Mvox/s", "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": f"{tiles} tiles of the reference's per-tile loop (74^3 in, 36^3 kept, batch 1, fp32) after 1 warm-up",
+            "ms_per_tile": dt / tiles * 1e3}
+
+
+def run_reference_inference(args, emit):
+    res = cpu_inference_sample(tiles=max(3, args.steps))
+    emit({"impl": "reference", "metric": "tiled_inference_mvox_per_s", "value": res["value"], "unit": "Mvox/s", "n_gpus": args.gpus,
+          "steps": max(3, args.steps), "warmup": 1, "ms_per_step": res["ms_per_tile"], "higher_is_better": True, "scaling": "strong",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "BASELINE config 5: predict_ng_cube tiling (74^3 tiles, stride 36), per-tile loop on the host cores",
+                     "sample": res["sample"]},
+          "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+          "e2e": {"value": res["value"], "unit": "Mvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
+def measure_inference(S, dev, rank, world, local, barrier, max_over_ranks, reps=2):
+    """BASELINE config 5: source uint8[(S+58)^3] (1082^3 for S = 1024; every 74^3 tile of the ceil(S/36)^3 grid in
+    bounds), start (19,19,19), size S^3, wf = 8, meanstd (0, 0.5774); reference tiling, z tile-layers sharded over the ranks with
+    no communication.  Device-resident AND end to end (pinned host slab -> H2D -> predict -> D2H of the rank's output slab)."""
+    import torch
+    from transfer_em_b200 import Engine
+    nt = (S + 35) // 36
+    V = nt * 36 + 38
+    ieng = Engine(dimsize=74, is3d=True, wf=WF, max_batch=64, train=False, device=local, seed=1234)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    vol = torch.randint(0, 256, (V, V, V), dtype=torch.uint8, device=dev, generator=g)
+    per, rem = divmod(nt, world)
+    zb = rank * per + min(rank, rem); ze = zb + per + (1 if rank < rem else 0)
+    out = torch.zeros((S, S, S), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    args = dict(tile_z_range=(zb, ze), out=out)
+    l0 = ieng.launch_count()
+    ieng.predict_volume(vol, (19, 19, 19), (S, S, S), MEANSTD_X, MEANSTD_Y, **args)     # warm-up (packs the weight images)
+    launches = ieng.launch_count() - l0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        ieng.predict_volume(vol, (19, 19, 19), (S, S, S), MEANSTD_X, MEANSTD_Y, **args)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    # end to end: this rank's source slab (tile layers zb..ze plus the 19-voxel halos) and output slab through pinned host memory
+    sz0, sz1 = 36 * zb, min(36 * ze + 38, V)
+    oz0, oz1 = 36 * zb, min(36 * ze, S)
+    h_src = vol[sz0:sz1].cpu().pin_memory()
+    h_out = torch.empty((max(oz1 - oz0, 0), S, S), dtype=torch.uint8).pin_memory()
+    vol2 = torch.zeros_like(vol)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(reps):
+        vol2[sz0:sz1].copy_(h_src, non_blocking=True)
+        ieng.predict_volume(vol2, (19, 19, 19), (S, S, S), MEANSTD_X, MEANSTD_Y, **args)
+        if oz1 > oz0:
+            h_out.copy_(out[oz0:oz1], non_blocking=True)
+        stream.synchronize()
+    e3.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / reps
+    ok = bool(oz1 <= oz0 or torch.equal(h_out, out[oz0:oz1].cpu()))
+    tiles = nt ** 3
+    by_tile, fl_tile = gen_forward_bytes(74, WF)
+    hbm, _, _, pk_src = peaks()
+    my_tiles = nt * nt * (ze - zb)
+    ach = tiles * by_tile / (ms * 1e-3) / 1e9 / world            # per-GPU algorithmic GB/s (the slowest rank sets ms)
+    res = {"metric": "tiled_inference_mvox_per_s", "value": S ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvox/s", "ms": ms,
+           "request": f"{S}^3 of a uint8 {V}^3 source (seed 7), start (19,19,19), reference tiling: {tiles} tiles of 74^3 at stride 36, "
+                      f"z tile-layers sharded over {world} GPU(s), no communication",
+           "tiles": tiles, "tiles_this_rank": my_tiles, "batch_tiles": 64, "gpu_launches": int(launches),
+           "e2e": {"value": S ** 3 / (ms_e2e * 1e-3) / 1e6, "unit": "Mvox/s", "ms": ms_e2e, "h2d_bytes_per_step": int(h_src.numel()) * world,
+                   "d2h_bytes_per_step": int(h_out.numel()) * world, "roundtrip_identical": ok},
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": pk_src,
+                        "algorithmic_bytes_per_tile": by_tile, "gflop_per_tile": fl_tile / 1e9,
+                        "note": "whole generator forward of a tile (12 fused layers, last layer writes uint8 into the stitched volume): "
+                                "algorithmic bytes of all tiles / wall time, per GPU"}}
+    del ieng, vol, vol2, out
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -172,7 +306,17 @@ def main():
     ap.add_argument("--infer-size", type=int, default=288, help="edge of the tiled-inference request (multiple of 36)")
     ap.add_argument("--wf", type=int, default=8, help="width divisor of the model (8 = BASELINE config 3; 1 = config 4, 64/128/256 channels)")
     ap.add_argument("--dim", type=int, default=74, help="patch edge (n = 2 mod 4; config 4 uses 110)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE config: 3 = train step at the default size (headline; the line also carries config 5 as `inference`), "
+                         "4 = largest programmable model (wf 1, 110^3, batch 4: one GPU's share of the 8-GPU job), 5 = tiled inference only")
     args = ap.parse_args()
+    if args.config == 4:
+        args.wf, args.dim, args.batch = 1, 110, 4
+        if args.steps == 20: args.steps = 3
+        if args.warmup == 5: args.warmup = 3
+        args.no_inference = True
+    if args.infer_size == 288 and not os.environ.get("TEM_BENCH_SMALL_INFER"):
+        args.infer_size = 1024
     # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -199,16 +343,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, args.warmup
-    model = EM2EM(DIM, "bench", is3d=True, wf=WF, max_batch=B, device=local, seed=1234, dropout=True,
-                  meanstd_x=MEANSTD_X, meanstd_y=MEANSTD_Y, distributed=world > 1,
-                  checkpoint_dir=os.path.join(tempfile.gettempdir(), "tem_bench_none"))
-    eng = model.engine
-    rng = np.random.default_rng(100 + rank)
-    NB = 4
-    host_x = [torch.from_numpy(synth_batch(rng, B, False)).pin_memory() for _ in range(NB)]
-    host_y = [torch.from_numpy(synth_batch(rng, B, True)).pin_memory() for _ in range(NB)]
-    dev_x = [t.to(dev) for t in host_x]; dev_y = [t.to(dev) for t in host_y]
-    stream = torch.cuda.current_stream()
 
     def barrier():
         if world > 1:
@@ -221,6 +355,38 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.config == 5:      # tiled inference as the headline line
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        inf = measure_inference(args.infer_size, dev, rank, world, local, barrier, max_over_ranks, reps=max(2, min(K, 5)))
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            cpu = None
+            if world == 1 and not args.no_cpu_baseline:
+                host_threads()
+                cpu = cpu_inference_sample(3)
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            emit({"metric": inf["metric"], "value": inf["value"], "unit": inf["unit"], "n_gpus": world, "steps": max(2, min(K, 5)), "warmup": 3,
+                  "ms_per_step": inf["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                  "config": {"workload": "BASELINE config 5: " + inf["request"], "wf": WF, "parallelism": f"z-slab x{world}",
+                             "l2": "1.27 GB source + 1.07 GB output + 1.2 GB of per-batch activations >> 126 MB L2",
+                             "warmup_note": "one full request is run before the timed ones (a request is thousands of launches)"},
+                  "e2e": inf["e2e"], "gpu_launches": inf["gpu_launches"], "clocks": clocks, "roofline": inf["roofline"], "cpu_baseline": cpu})
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    model = EM2EM(DIM, "bench", is3d=True, wf=WF, max_batch=B, device=local, seed=1234, dropout=True,
+                  meanstd_x=MEANSTD_X, meanstd_y=MEANSTD_Y, distributed=world > 1,
+                  checkpoint_dir=os.path.join(tempfile.gettempdir(), "tem_bench_none"))
+    eng = model.engine
+    rng = np.random.default_rng(100 + rank)
+    NB = 4
+    host_x = [torch.from_numpy(synth_batch(rng, B, False)).pin_memory() for _ in range(NB)]
+    host_y = [torch.from_numpy(synth_batch(rng, B, True)).pin_memory() for _ in range(NB)]
+    dev_x = [t.to(dev) for t in host_x]; dev_y = [t.to(dev) for t in host_y]
+    stream = torch.cuda.current_stream()
 
     # ---- device-resident throughput ------------------------------------------------------------
     for i in range(W):
@@ -287,7 +453,8 @@ def main():
         if caps:
             c = max(caps, key=lambda c: rep[c["tag"]]["bytes"])
             traffic = c["dram_bytes_per_launch"]
-            traffic_of = {"layer": c["tag"], "algorithmic_bytes": rep[c["tag"]]["bytes"], "capture": "profiles/ncu_r1_" + c["capture"] + ".txt"}
+            traffic_of = {"layer": c["tag"], "algorithmic_bytes": rep[c["tag"]]["bytes"], "capture": "profiles/" + c["capture"] + ".txt",
+                          "captured_at_commit": json.load(open(tp)).get("commit")}
     # which roofline bounds the dominant kernel: its arithmetic intensity against the ridge of the measured peaks (the wf = 8
     # layers of config 3 sit below it: HBM; the 64-256 channel layers of config 4 far above: bf16 tensor cores)
     tensor_bound = t["flops"] / max(t["bytes"], 1.0) > (tf_sus * 1e12) / (hbm * 1e9)
@@ -318,33 +485,20 @@ def main():
     kernels = [{"tag": k, "ms_per_step": v["ms"] / PK, "gbs": v["bytes"] * v["count"] / (v["ms"] * 1e-3) / 1e9,
                 "tflops": v["flops"] * v["count"] / (v["ms"] * 1e-3) / 1e12} for k, v in top5]
 
-    # ---- secondary metric: tiled inference (predict_ng_cube tiling, device resident) -----------------
+    # ---- BASELINE config 5 beside the headline: tiled inference of a large subvolume, z-slab sharded --------------
     inference = None
     if not args.no_inference:
         del model, eng
         torch.cuda.empty_cache()
-        from transfer_em_b200 import Engine
-        ieng = Engine(dimsize=DIM, is3d=True, wf=WF, max_batch=64, train=False, device=local, seed=1234)
-        S = args.infer_size
-        vol = torch.randint(0, 256, (S + 38, S + 38, S + 38), dtype=torch.uint8, device=dev)
-        nz = (S + 35) // 36
-        per, rem = divmod(nz, world)
-        zb = rank * per + min(rank, rem); ze = zb + per + (1 if rank < rem else 0)
-        out = torch.zeros((S, S, S), dtype=torch.uint8, device=dev)
-        ieng.predict_volume(vol, (19, 19, 19), (S, S, S), MEANSTD_X, MEANSTD_Y, tile_z_range=(zb, ze), out=out)   # warm-up
-        barrier()
-        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e4.record(stream)
-        ieng.predict_volume(vol, (19, 19, 19), (S, S, S), MEANSTD_X, MEANSTD_Y, tile_z_range=(zb, ze), out=out)
-        e5.record(stream)
-        barrier()
-        ms_inf = max_over_ranks(e4.elapsed_time(e5))
-        inference = {"metric": "tiled_inference_mvox_per_s", "value": S ** 3 / (ms_inf * 1e-3) / 1e6, "unit": "Mvox/s",
-                     "request": f"{S}^3 uint8 (reference tiling: 74^3 tiles, stride 36), z-slab sharded over {world} GPU(s)",
-                     "tiles": ((S + 35) // 36) ** 3, "ms": ms_inf}
+        inference = measure_inference(args.infer_size, dev, rank, world, local, barrier, max_over_ranks)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            host_threads()
+            c = cpu_inference_sample(3)
+            inference["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        host_threads()
         cpu_baseline = cpu_train_sample(steps=4, warmup=1, B=1)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

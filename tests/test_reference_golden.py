@@ -19,9 +19,14 @@ PROBE_SEED = 977
 NETS = ("g", "f", "dx", "dy")
 
 
-def gold(name):
-    p = os.path.join(GOLD, name)
+PREFIXES = ["ref", "tf"]      # ref_: reference code on oracle/tf_shim (committed); tf_: reference code on real TensorFlow (when provided)
+
+
+def gold(name, prefix="ref"):
+    p = os.path.join(GOLD, f"{prefix}_{name}")
     if not os.path.exists(p):
+        if prefix == "tf":
+            pytest.skip("no real-TensorFlow golden (tools/make_reference_golden.py --real-tf needs a TensorFlow install)")
         pytest.fail(f"{p} is missing: run tools/make_reference_golden.py where /root/reference exists")
     return np.load(p)
 
@@ -63,8 +68,9 @@ def check_weights_checksum(z, P):
     np.testing.assert_allclose(cs, z["weights_checksum"], rtol=1e-12)      # the recipe regenerates the golden's weights
 
 
-def test_structure_matches_reference_builders():
-    z = gold("ref_structure.npz")
+@pytest.mark.parametrize("prefix", PREFIXES)
+def test_structure_matches_reference_builders(prefix):
+    z = gold("structure.npz", prefix)
     for is3d, tag in ((True, "3d"), (False, "2d")):
         for k, layers in (("g", O.generator_layers(8)), ("dx", O.discriminator_layers(8, is3d))):
             shapes = []
@@ -94,8 +100,9 @@ def test_structure_matches_reference_builders():
             unet_generator(d)                               # generator.py:37-38
 
 
-def test_uint8_conventions_match_reference_functions():
-    z = gold("ref_conversions.npz")
+@pytest.mark.parametrize("prefix", PREFIXES)
+def test_uint8_conventions_match_reference_functions(prefix):
+    z = gold("conversions.npz", prefix)
     u = np.arange(256, dtype=np.uint8)
     for i in range(4):
         got = O.standardize_population(O.scale_tensor(u), tuple(z[f"ms_{i}"]))[:, 0]
@@ -115,8 +122,9 @@ def test_uint8_conventions_match_reference_functions():
     np.testing.assert_allclose(rmse, float(z["accuracy"]), rtol=1e-6)
 
 
-def test_predict_ng_cube_indexing_bit_exact_vs_reference():
-    z = gold("ref_predict_ng_cube.npz")
+@pytest.mark.parametrize("prefix", PREFIXES)
+def test_predict_ng_cube_indexing_bit_exact_vs_reference(prefix):
+    z = gold("predict_ng_cube.npz", prefix)
     vol = np.random.default_rng(int(z["vol_seed"])).integers(0, 256, (110, 110, 110), dtype=np.uint8)
     start, size = tuple(int(v) for v in z["start"]), tuple(int(v) for v in z["size"])
     ms_x, ms_y = tuple(z["ms_x"]), tuple(z["ms_y"])
@@ -138,9 +146,12 @@ def test_predict_ng_cube_indexing_bit_exact_vs_reference():
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+@pytest.mark.parametrize("prefix", PREFIXES)
 @pytest.mark.parametrize("name", ["2d", "3d", "3d_dropout"])
-def test_train_step_matches_reference_train_step(name):
-    z = gold(f"ref_train_{name}.npz")
+def test_train_step_matches_reference_train_step(name, prefix):
+    if prefix == "tf" and name == "3d_dropout":
+        pytest.skip("mask injection needs the shim's Dropout layer")
+    z = gold(f"train_{name}.npz", prefix)
     is3d, B, seed, scale, wf = bool(z["is3d"]), int(z["B"]), int(z["seed"]), float(z["scale"]), int(z["wf"])
     P = params_for(wf, is3d, seed, scale)
     check_weights_checksum(z, P)

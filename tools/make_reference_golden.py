@@ -1,5 +1,13 @@
 #!/usr/bin/env python
-"""Generate tests/golden/ref_*.npz by running the REFERENCE'S OWN Python (/root/reference/transfer_em) in this container.
+"""Generate tests/golden/{ref,tf}_*.npz by running the REFERENCE'S OWN Python (/root/reference/transfer_em).
+
+Two modes, one schema:
+  python tools/make_reference_golden.py              build container: the reference runs on oracle/tf_shim -> tests/golden/ref_*.npz
+  python tools/make_reference_golden.py --real-tf    anywhere tensorflow 2.x + tensorflow_addons are installed (TEM_REFERENCE points to
+                                                     the reference checkout): the reference runs on REAL TensorFlow, eagerly
+                                                     -> tests/golden/tf_*.npz, which pin parity against TensorFlow's own kernels
+tests/test_reference_golden.py (oracle, CPU) and tests/test_gpu_golden.py (CUDA path) check every prefix that is present; the
+tf_ files cannot be produced in the build image (no TensorFlow wheel, no network) and are skipped while absent.
 
 TensorFlow / tensorflow_addons are not installable here, so the reference is imported on top of oracle/tf_shim (a
 torch-CPU stand-in for the few dozen TF symbols its hot path touches; see oracle/tf_shim/tensorflow/__init__.py for what
@@ -19,7 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("TEM_REFERENCE", "/root/reference")
-sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_shim"))
+REAL_TF = "--real-tf" in sys.argv
+if not REAL_TF:
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "tf_shim"))
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
@@ -30,6 +40,20 @@ from transfer_em import utils as ref_utils          # noqa: E402
 from transfer_em.datasets import datasets as ref_ds  # noqa: E402
 from transfer_em import debug as ref_debug          # noqa: E402
 from oracle import tem_oracle as O                  # noqa: E402  (only for init_params / the dropout hash)
+
+PREFIX = "tf" if REAL_TF else "ref"
+if REAL_TF:
+    tf.config.run_functions_eagerly(True)           # train_step is a @tf.function: the gradient recorder needs eager tensors
+    tf.random.set_seed(0)
+    _t = tf.constant
+else:
+    _t = tf._t
+
+
+def to_np(t):
+    if hasattr(t, "detach"):
+        return t.detach().numpy()
+    return t.numpy() if hasattr(t, "numpy") else np.asarray(t)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 NETS = (("g", "generator_g"), ("f", "generator_f"), ("dx", "discriminator_x"), ("dy", "discriminator_y"))
@@ -83,13 +107,16 @@ class GradRecorder:
 
     def apply(self, gv):
         gv = list(gv)
-        self.last = [None if g is None else g.detach().numpy().copy() for g, _ in gv]
+        self.last = [None if g is None else to_np(g).copy() for g, _ in gv]
         self._orig(gv)
 
 
 def train_case(name, is3d, B, seed, scale, wf=8, keys=None, steps=3, store_full_grads=True):
-    tf.DROPOUT.update(enabled=keys is not None, keys=keys, calls=0,
-                      mask_fn=lambda key, shape: O.dropout_keep_mask(key, shape))
+    if REAL_TF and keys is not None:
+        return                          # mask injection needs the shim's Dropout layer
+    if not REAL_TF:
+        tf.DROPOUT.update(enabled=keys is not None, keys=keys, calls=0,
+                          mask_fn=lambda key, shape: O.dropout_keep_mask(key, shape))
     model = EM2EM(74, f"golden_{name}", is3d=is3d, wf=wf)
     P = params_for(wf, is3d, seed, scale)
     load_into_reference(model, P, is3d)
@@ -106,7 +133,7 @@ def train_case(name, is3d, B, seed, scale, wf=8, keys=None, steps=3, store_full_
         if keys is not None:
             tf.DROPOUT["calls"] = 0              # the same 12 masks every step (the CUDA test re-injects the same keys)
         before = {k: getattr(model, attr).get_weights() for k, attr in NETS}
-        l = model.train_step(tf._t(rx), tf._t(ry))
+        l = model.train_step(_t(rx), _t(ry))
         losses.append([float(v) for v in l])
         after = {k: getattr(model, attr).get_weights() for k, attr in NETS}
         for k, _ in NETS:
@@ -123,10 +150,11 @@ def train_case(name, is3d, B, seed, scale, wf=8, keys=None, steps=3, store_full_
                         m = float(np.abs(gi).max()) or 1.0
                         out[f"grad16_{k}_{i}"] = (gi / m).astype(np.float16); out[f"gradmax_{k}_{i}"] = np.float64(m)
     out["losses"] = np.array(losses, np.float64)
-    tf.DROPOUT.update(enabled=False, keys=None)
-    y = model.predict(tf._t(rx))                                       # cgan.py:289-293 after `steps` updates
-    out["predict_after"] = np.asarray(y.numpy() if hasattr(y, "numpy") else y, np.float32)[:1, ::3, ::3]
-    np.savez_compressed(os.path.join(GOLD, f"ref_train_{name}.npz"), **out)
+    if not REAL_TF:
+        tf.DROPOUT.update(enabled=False, keys=None)
+    y = model.predict(_t(rx))                                          # cgan.py:289-293 after `steps` updates
+    out["predict_after"] = np.asarray(to_np(y), np.float32)[:1, ::3, ::3]
+    np.savez_compressed(os.path.join(GOLD, f"{PREFIX}_train_{name}.npz"), **out)
     print(name, "losses step 1:", losses[0])
 
 
@@ -141,7 +169,7 @@ class _MemDataset:
         s = self.size
         for (x, y, z) in self.rois:
             cube = self.vol[z:z + s, y:y + s, x:x + s]
-            t = ref_ds.scale_tensor(tf._t(cube.copy()))
+            t = ref_ds.scale_tensor(_t(cube.copy()))
             t = ref_ds.standardize_population(t, self.meanstd)
             yield tf.expand_dims(t, 0)
 
@@ -164,8 +192,8 @@ class _ExactModel:
     outdimsize, buffer = 40, 17
 
     def predict(self, x):
-        a = np.asarray(x.numpy() if hasattr(x, "numpy") else x, np.float32)
-        return tf._t(np.float32(0.5) * a[:, 17:-17, 17:-17, 17:-17, :] + np.float32(0.1))
+        a = np.asarray(to_np(x), np.float32)
+        return _t(np.float32(0.5) * a[:, 17:-17, 17:-17, 17:-17, :] + np.float32(0.1))
 
 
 def tiling_cases():
@@ -180,15 +208,15 @@ def tiling_cases():
     model = EM2EM(74, "golden_tile", is3d=True, wf=8)
     P = params_for(8, True, 33, 5.0)
     load_into_reference(model, P, True)
-    probe = model.generator_g(tf._t(np.random.default_rng(1).standard_normal((1, 74, 74, 74, 1)).astype(np.float32)))
+    probe = model.generator_g(_t(np.random.default_rng(1).standard_normal((1, 74, 74, 74, 1)).astype(np.float32)))
     g = model.generator_g.get_weights()
-    k11 = np.float32(0.8 / float(probe.std()))
+    k11 = np.float32(0.8 / float(np.std(to_np(probe))))
     g[11] = (g[11] * k11).astype(np.float32)
     model.generator_g.set_weights(g)
     res["g11_scale"] = np.float64(k11)
     with torch.no_grad():
         res["gen_out"] = run_reference_predict_ng_cube(vol, start, size, model, ms_x, ms_y, False)
-    np.savez_compressed(os.path.join(GOLD, "ref_predict_ng_cube.npz"), **res)
+    np.savez_compressed(os.path.join(GOLD, f"{PREFIX}_predict_ng_cube.npz"), **res)
     print("predict_ng_cube goldens:", out.shape, res["gen_out"].shape)
 
 
@@ -196,19 +224,19 @@ def conversion_cases():
     u = np.arange(256, dtype=np.uint8)
     out = {}
     for i, ms in enumerate([(0.0, 1.0), (0.0, 0.5774), (0.02, 0.55), (-0.113, 0.731)]):
-        t = ref_ds.standardize_population(ref_ds.scale_tensor(tf._t(u.copy())), ms)
-        out[f"std_{i}"] = t.numpy()[:, 0]; out[f"ms_{i}"] = np.array(ms)
+        t = ref_ds.standardize_population(ref_ds.scale_tensor(_t(u.copy())), ms)
+        out[f"std_{i}"] = to_np(t)[:, 0]; out[f"ms_{i}"] = np.array(ms)
     # the uint8 conversion of utils.py:109,118 on a dense sweep that includes .5 ties and out-of-range values (wraps)
     y = np.concatenate([np.linspace(-3.5, 3.5, 4001), (np.arange(-40, 300) + 0.5) / 127.5 / 0.4 - (1 + 0.03) / 0.4]).astype(np.float32)
     ms_y = (0.03, 0.4)
-    v = (ref_ds.unstandardize_population(tf._t(y.copy()), ms_y) + 1) * 127.5
+    v = to_np((ref_ds.unstandardize_population(_t(y.copy()), ms_y) + 1) * 127.5)
     out["y_sweep"] = y; out["ms_y"] = np.array(ms_y)
-    out["y_u8"] = np.around(v.numpy()).astype(np.uint8)
-    out["y_trunc"] = v.numpy().astype(np.uint8)              # the fetch_input path truncates (utils.py:123-125)
+    out["y_u8"] = np.around(v).astype(np.uint8)
+    out["y_trunc"] = v.astype(np.uint8)                      # the fetch_input path truncates (utils.py:123-125)
     # get_meanstd (datasets.py:173-190)
     r = np.random.default_rng(5)
     tensors = [r.standard_normal((9, 11, 13, 1)).astype(np.float32) * (1 + 0.1 * i) + 0.01 * i for i in range(5)]
-    m, s = ref_ds.get_meanstd([tf._t(t) for t in tensors])
+    m, s = ref_ds.get_meanstd([_t(t) for t in tensors])
     out["meanstd"] = np.array([float(m), float(s)])
     # warp_tensor (debug.py:7-63) with the hole seeds fixed, and accuracy (debug.py:65-71)
     for nd, shape in ((3, (12, 14, 16, 1)), (2, (20, 24, 1))):
@@ -216,12 +244,12 @@ def conversion_cases():
         uni = r.uniform(0, 1, int(np.prod(shape))).astype(np.float32)
         uni[:: 97] = 1e-5                                   # make sure some holes are seeded at this small size
         orig = tf.random.uniform
-        tf.random.uniform = lambda shp, lo=0.0, hi=1.0: tf._t(uni.copy())
-        w = ref_debug.warp_tensor(tf._t(t.copy()))
+        tf.random.uniform = lambda shp, lo=0.0, hi=1.0: _t(uni.copy())
+        w = ref_debug.warp_tensor(_t(t.copy()))
         tf.random.uniform = orig
-        out[f"warp_in_{nd}"] = t; out[f"warp_uniform_{nd}"] = uni; out[f"warp_out_{nd}"] = w.numpy()
-    out["accuracy"] = np.float64(ref_debug.accuracy(tf._t(out["warp_in_3"]), tf._t(out["warp_out_3"])))
-    np.savez_compressed(os.path.join(GOLD, "ref_conversions.npz"), **out)
+        out[f"warp_in_{nd}"] = t; out[f"warp_uniform_{nd}"] = uni; out[f"warp_out_{nd}"] = to_np(w)
+    out["accuracy"] = np.float64(ref_debug.accuracy(_t(out["warp_in_3"]), _t(out["warp_out_3"])))
+    np.savez_compressed(os.path.join(GOLD, f"{PREFIX}_conversions.npz"), **out)
     print("conversion goldens written")
 
 
@@ -237,9 +265,9 @@ def structure_case():
             out[f"count_{k}_{tag}"] = np.int64(sum(int(np.prod(s)) for s in shapes))
         out[f"buffer_{tag}"] = np.int64(m.buffer); out[f"outdimsize_{tag}"] = np.int64(m.outdimsize)
         n = 74
-        x = tf._t(np.zeros((1,) + (n,) * (3 if is3d else 2) + (1,), np.float32))
+        x = _t(np.zeros((1,) + (n,) * (3 if is3d else 2) + (1,), np.float32))
         out[f"gen_out_shape_{tag}"] = np.array(m.generator_g(x).shape)
-        out[f"disc_out_shape_{tag}"] = np.array(m.discriminator_x(tf._t(np.zeros((1,) + (40,) * (3 if is3d else 2) + (1,), np.float32))).shape)
+        out[f"disc_out_shape_{tag}"] = np.array(m.discriminator_x(_t(np.zeros((1,) + (40,) * (3 if is3d else 2) + (1,), np.float32))).shape)
     errs = []
     for d in (70, 76, 132):
         try:
@@ -248,7 +276,7 @@ def structure_case():
         except RuntimeError:
             errs.append(1)
     out["raises_runtime_error_70_76_132"] = np.array(errs)
-    np.savez_compressed(os.path.join(GOLD, "ref_structure.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, f"{PREFIX}_structure.npz"), **out)
     print("structure goldens written", {k: v for k, v in out.items() if k.startswith("count")})
 
 

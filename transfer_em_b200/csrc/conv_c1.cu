@@ -197,6 +197,13 @@ __global__ void __launch_bounds__(256) conv_c1out_kernel(const ConvArgs a, const
     if (oz_ >= a.L[0]) break;
     float v = acc[j];
     if (a.slope != 1.f) v = v > 0.f ? v : v * a.slope;
+    if (a.st_out) {            // tiled inference: straight into the stitched uint8 volume (utils.py:109-121)
+      const int cz = oz_ - a.st_tpad, cy = oy_ - a.st_tpad, cx = ox_ - a.st_tpad;
+      if (cz < 0 || cz >= a.st_od || cy < 0 || cy >= a.st_od || cx < 0 || cx >= a.st_od) continue;
+      const long long gx = a.st_index[b * 3 + 0] + cx, gy = a.st_index[b * 3 + 1] + cy, gz = a.st_index[b * 3 + 2] + cz;
+      if (gx < a.st_OX && gy < a.st_OY && gz < a.st_OZ) a.st_out[(gz * a.st_OY + gy) * a.st_OX + gx] = tem_to_u8_round(v, a.st_mean, a.st_std);
+      continue;
+    }
     float* op = out + ((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff;
     *op = a.accumulate ? *op + v : v;
   }

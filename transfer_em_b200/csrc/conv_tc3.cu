@@ -216,6 +216,11 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       const int oy = y0 + yl, ox = x0 + xl;
       const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
       uint4 refq[PF][CP / 8];
+      // per-item bases: the per-slice part of every address is one multiply-add (index arithmetic hoisted out of the slice loop)
+      const long long out_zstride = (long long)a.OY * a.OX * a.out_C;
+      bf16* const out_base = a.out + ((((long long)b * a.OZ + z0 + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
+      const uint32_t di_base = (uint32_t)(((((long long)b * a.L[0] + z0) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
+      const uint32_t di_zstride = (uint32_t)(a.L[1] * a.L[2] * a.Cout);
       const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
       auto fetch_ref = [&](int zo, uint4* qv) {
         if (a.ref && inside && zo < nz) {
@@ -230,7 +235,6 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
         for (int pu = 0; pu < PF; ++pu) {
           const int zo = zb + 2 * pu + ew;
           if (zo >= nz) break;
-          const int oz = z0 + zo;
           // output slice zo has its three kz parts once input slice zo + 2 has been multiplied.  CP == 8: the MMA of input
           // slice zo + 3 still touches this column group (the fourth, zero-weight group of N = 32 adds 0 to it) and would
           // write a stale value back over the re-zeroed columns, so that step must have retired as well
@@ -261,11 +265,11 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           }
           fetch_ref(zo + 2 * PF, refq[pu]);
           if (a.drop_key) {
-            const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
+            const uint32_t di = di_base + (uint32_t)zo * di_zstride;
 #pragma unroll
             for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
           }
-          bf16* op = a.out + ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
+          bf16* op = out_base + (long long)zo * out_zstride;
 #pragma unroll
           for (int c = 0; c < CP; c += 8) {
             if (c < a.Cout) {

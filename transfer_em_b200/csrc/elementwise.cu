@@ -122,20 +122,9 @@ __global__ void standardize_u8_kernel(const uint8_t* in, float* out, long long n
     out[i] = tem_standardize((float)in[i], mean, stdv);
 }
 
-__device__ __forceinline__ uint8_t to_u8_round(float y, float mean, float stdv) {
-  // (y*std + mean + 1) * 127.5 -> np.around -> astype(uint8) wrap   (utils.py:109,118; datasets.py:165-171)
-  float v = __fmul_rn(y, stdv);
-  v = __fadd_rn(v, mean);
-  v = __fadd_rn(v, 1.0f);
-  v = __fmul_rn(v, 127.5f);
-  const float r = rintf(v);
-  const long long q = (long long)r;
-  return (uint8_t)(q & 0xFF);
-}
-
 __global__ void unstandardize_u8_kernel(const float* in, uint8_t* out, long long n, float mean, float stdv) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = to_u8_round(in[i], mean, stdv);
+    out[i] = tem_to_u8_round(in[i], mean, stdv);
 }
 
 __global__ void dropout_mask_kernel(uint32_t key, float* out, long long n) {
@@ -179,7 +168,7 @@ __global__ void stitch_u8_kernel(const StitchArgs a) {
     const long long ox = a.index[tile * 3 + 0] + x, oy = a.index[tile * 3 + 1] + y, oz = a.index[tile * 3 + 2] + z;
     if (ox >= a.OX || oy >= a.OY || oz >= a.OZ) continue;
     const long long yo = (((long long)tile * a.ydim + z + a.tpad) * a.ydim + y + a.tpad) * a.ydim + x + a.tpad;
-    a.out[(oz * a.OY + oy) * a.OX + ox] = to_u8_round(a.y[yo], a.mean, a.stdv);
+    a.out[(oz * a.OY + oy) * a.OX + ox] = tem_to_u8_round(a.y[yo], a.mean, a.stdv);
   }
 }
 

@@ -45,6 +45,9 @@ struct ConvArgs {
   uint32_t drop_key;   // != 0: multiply by 2*keep(hash(idx ^ key)), idx = dense [B,L,Cout] index
   int accumulate;      // out += result
   int use_lut; float lut_mean, lut_std;   // u8 input: (u/127.5 - 1 - mean)/std
+  // fused inference epilogue of the Cout = 1 last generator layer (transfer_em/utils.py:109-121): un-standardise, crop tpad,
+  // round-half-even, uint8 wrap, scatter tile b to its place in the stitched volume.  st_out == nullptr: plain output
+  uint8_t* st_out; const int* st_index; int st_tpad, st_od; float st_mean, st_std; long long st_OZ, st_OY, st_OX;
   int ci_chunk;
   long long nvox;      // voxels per parity class
   int H[3];            // per-class extents (ceil(L/stride) for form 1, L for form 0)
@@ -83,6 +86,16 @@ __device__ __forceinline__ float tem_standardize(float u, float mean, float stdv
   return __fdiv_rn(t, stdv);
 }
 __device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ uint8_t tem_to_u8_round(float y, float mean, float stdv) {
+  // (y*std + mean + 1) * 127.5 -> np.around -> astype(uint8) wrap   (utils.py:109,118; datasets.py:165-171), op order kept
+  float v = __fmul_rn(y, stdv);
+  v = __fadd_rn(v, mean);
+  v = __fadd_rn(v, 1.0f);
+  v = __fmul_rn(v, 127.5f);
+  const float r = rintf(v);
+  const long long q = (long long)r;
+  return (uint8_t)(q & 0xFF);
+}
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll

@@ -259,7 +259,7 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
 // forward of one layer: out = act(dropout(conv(cat(s0,s1)) + bias))
 static int run_forward(const tem_handle* h, const LayerSpec& L, const float* netp, const SrcView& s0, int C0,
                        const SrcView* s1, int C1, const Tensor& out, int B, uint32_t drop_key,
-                       int use_lut, float mean, float stdv, cudaStream_t st) {
+                       int use_lut, float mean, float stdv, cudaStream_t st, const StitchArgs* stitch = nullptr, bool* stitched = nullptr) {
   ConvArgs a; memset(&a, 0, sizeof(a));
   a.s0 = s0; a.C0 = C0; a.C1 = C1; if (s1) a.s1 = *s1;
   a.w = netp + L.w_off; a.bias = L.bias ? netp + L.b_off : nullptr;
@@ -270,6 +270,13 @@ static int run_forward(const tem_handle* h, const LayerSpec& L, const float* net
   set_out(a, out, 0, nullptr);
   a.Cout = L.cout; a.slope = L.slope; a.drop_key = L.dropout ? drop_key : 0;
   a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
+  if (stitched) *stitched = false;
+  if (stitch && h->cfg.use_tensor_cores && L.cout == 1 && C0 <= 32 && !getenv("TEM_NO_CONV_C1") && !getenv("TEM_NO_FUSED_STITCH") && conv_c1_supported(a)) {
+    // the single-channel last layer writes uint8 straight into the stitched volume (the fp32 tile output is never stored)
+    a.st_out = stitch->out; a.st_index = stitch->index; a.st_tpad = stitch->tpad; a.st_od = stitch->od;
+    a.st_mean = stitch->mean; a.st_std = stitch->stdv; a.st_OZ = stitch->OZ; a.st_OY = stitch->OY; a.st_OX = stitch->OX;
+    if (stitched) *stitched = true;
+  }
   {
     const double ovox = (double)B * out.d[0] * out.d[1] * out.d[2];
     const double ivox = (double)B * ((double)s0.Z * s0.Y * s0.X);
@@ -372,7 +379,8 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
 // ------------------------------------------------------------------------------------------
 // generator passes
 // ------------------------------------------------------------------------------------------
-static int gen_forward(tem_handle* h, int net, GenPass& P, const InputRef& in, int B, int n, const uint32_t keys[2], cudaStream_t st) {
+static int gen_forward(tem_handle* h, int net, GenPass& P, const InputRef& in, int B, int n, const uint32_t keys[2], cudaStream_t st,
+                       const StitchArgs* stitch = nullptr, bool* stitched = nullptr) {
   const NetSpec& N = h->nets[net];
   const float* w = h->params + N.arena_off;
   int d[12]; gen_dims(n, d);
@@ -394,7 +402,7 @@ static int gen_forward(tem_handle* h, int net, GenPass& P, const InputRef& in, i
     SrcView s1 = view_of(P.a[1]); axes(h, crop0, 0, s1.shift);
     TEM_CHECK(run_forward(h, N.L[10], w, view_of(P.a[9]), N.L[9].cout, &s1, N.L[1].cout, P.a[10], B, 0, 0, 0, 0, st));
   }
-  TEM_CHECK(run_forward(h, N.L[11], w, view_of(P.a[10]), N.L[11].cin, nullptr, 0, P.a[11], B, 0, 0, 0, 0, st));
+  TEM_CHECK(run_forward(h, N.L[11], w, view_of(P.a[10]), N.L[11].cin, nullptr, 0, P.a[11], B, 0, 0, 0, 0, st, stitch, stitched));
   return TEM_OK;
 }
 
@@ -1147,11 +1155,12 @@ extern "C" int tem_predict_volume(tem_handle* h, int net, const uint8_t* vol, co
     const int* d_orig = h->tile_origins + done * 3;
     const int* d_idx = h->tile_index + done * 3;
     ir.origins = d_orig;
-    TEM_CHECK(gen_forward(h, net, P, ir, nb, tsz, nullptr, st));
     StitchArgs sa; memset(&sa, 0, sizeof(sa));
     sa.y = (const float*)P.a[11].p; sa.index = d_idx; sa.T = nb; sa.ydim = od + 2 * tpad; sa.tpad = tpad; sa.od = od;
     sa.mean = msy[0]; sa.stdv = msy[1]; sa.out = out; sa.OZ = size[2]; sa.OY = size[1]; sa.OX = size[0];
-    TEM_CUDA(launch_stitch_u8(sa, st));
+    bool stitched = false;
+    TEM_CHECK(gen_forward(h, net, P, ir, nb, tsz, nullptr, st, &sa, &stitched));
+    if (!stitched) TEM_CUDA(launch_stitch_u8(sa, st));      // models whose last layer does not run on the fused kernel
     if (in_out) {
       FetchInArgs fa; memset(&fa, 0, sizeof(fa));
       fa.vol = vol; fa.VZ = vd[0]; fa.VY = vd[1]; fa.VX = vd[2]; fa.origins = d_orig; fa.index = d_idx;
