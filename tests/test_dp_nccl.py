@@ -28,7 +28,8 @@ def test_dp_gradients_equal_global_batch(is3d):
     with open(os.path.join(ROOT, "gpurun_out", f"dp_nccl_{'3d' if is3d else '2d'}.json"), "w") as f:
         json.dump(res, f)
     assert res["replicas_bit_identical"] and res["step"] == 3
-    # fp32 atomics order differs between a batch-1 and a batch-2 launch: 1e-5 is summation noise, not a scaling error
-    assert max(res["grad_rel_l2"].values()) < 1e-4, res
+    # fp32 atomics order differs between a batch-1 and a batch-2 launch: summation noise, not a scaling error
+    # (measured on 2 x B200, profiles/dp_nccl_r2.log: 3-D 3e-7, 2-D 3e-5 on the direct-kernel discriminators)
+    assert max(res["grad_rel_l2"].values()) < (1e-5 if is3d else 1e-4), res
     assert res["loss_rel"] < 1e-5, res
     assert max(res["params_vs_single_rel_l2"].values()) < 2e-2, res      # Adam's sign-like first steps amplify 1e-5 gradient noise
