@@ -39,6 +39,8 @@ struct Tc3Args {
   int items, nbmax;            // work items (persistent CTAs loop over them), pipeline steps of the longest item
   int sb;                      // input slices per pipeline step: one full / empty / tfull barrier round trip per sb slices
   bf16* out; int OZ, OY, OX, out_C, out_coff, out_off[3];
+  int out_f32;                 // Cout == 1 (last generator layer): channel 0 leaves as fp32, or, with st_out, as uint8 into the stitched volume
+  uint8_t* st_out; const int* st_index; int st_tpad, st_od; float st_mean, st_std; long long st_OZ, st_OY, st_OX;
   int Cout;
   float slope;
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
@@ -269,6 +271,20 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
             for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
           }
+          if (CP == 8 && a.out_f32) {           // g11 (16 -> 1, linear): one fp32 value per voxel, or the fused inference epilogue of utils.py:109-121
+            const float y = a.slope != 1.f ? (v[0] > 0.f ? v[0] : v[0] * a.slope) : v[0];
+            const int oz = z0 + zo;
+            if (a.st_out) {
+              const int cz = oz - a.st_tpad, cy = oy - a.st_tpad, cx = ox - a.st_tpad;
+              if (cz >= 0 && cz < a.st_od && cy >= 0 && cy < a.st_od && cx >= 0 && cx < a.st_od) {
+                const long long gx = a.st_index[b * 3 + 0] + cx, gy = a.st_index[b * 3 + 1] + cy, gz = a.st_index[b * 3 + 2] + cz;
+                if (gx < a.st_OX && gy < a.st_OY && gz < a.st_OZ) a.st_out[(gz * a.st_OY + gy) * a.st_OX + gx] = tem_to_u8_round(y, a.st_mean, a.st_std);
+              }
+            } else {
+              reinterpret_cast<float*>(a.out)[((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff] = y;
+            }
+            continue;
+          }
           bf16* op = out_base + (long long)zo * out_zstride;
 #pragma unroll
           for (int c = 0; c < CP; c += 8) {
@@ -355,13 +371,15 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (a.form != 0 && !(a.form == 1 && a.stride[0] == 1 && a.stride[1] == 1 && a.stride[2] == 1)) return false;
   if (a.k[0] != 3 || a.k[1] != 3 || a.k[2] != 3) return false;
   if (a.stride[0] != 1 || a.stride[1] != 1 || a.stride[2] != 1) return false;
-  if (a.s0.dtype != DT_BF16 || a.out_dtype != DT_BF16) return false;
+  const bool last = a.Cout == 1 && a.out_dtype == DT_F32 && a.form == 0 && !a.ref && !a.drop_key && !a.accumulate && a.C0 + a.C1 <= 32;   // g11: 16 -> 1, fp32 / fused uint8 output
+  if (a.s0.dtype != DT_BF16 || (a.out_dtype != DT_BF16 && !last)) return false;
   if (a.s0.origins || a.use_lut || a.bias) return false;
   const int cin = a.C0 + a.C1;
   if (!(cin == 8 || cin % 16 == 0)) return false;
   if (a.C0 % 8 || a.C1 % 8 || a.s0.C % 8 || a.s0.coff != 0 || a.s0.C != a.C0) return false;
   if (a.C1 && (a.s1.dtype != DT_BF16 || a.s1.C % 8 || a.s1.coff != 0 || a.s1.C != a.C1)) return false;
-  if (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8) return false;
+  if (!last && (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8)) return false;
+  if (a.st_out && !last) return false;
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
   const size_t smem = ((tc3_packed_bytes(cin, a.Cout) + 1023) & ~(size_t)1023) + (size_t)2 * sb_of(cin == 8 ? 5 : 9 * (cin / 16)) * (cin / 8) * PLANE_STRIDE + 1024;   // two pipeline steps at least
   if (smem > 200 * 1024) return false;
@@ -413,6 +431,9 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
   for (int i = 0; i < 3; ++i) { t.out_off[i] = a.out_off[i]; t.ref_off[i] = a.ref_off[i]; }
   t.Cout = a.Cout; t.slope = a.slope;
+  t.out_f32 = a.out_dtype == DT_F32;
+  t.st_out = a.st_out; t.st_index = a.st_index; t.st_tpad = a.st_tpad; t.st_od = a.st_od; t.st_mean = a.st_mean; t.st_std = a.st_std;
+  t.st_OZ = a.st_OZ; t.st_OY = a.st_OY; t.st_OX = a.st_OX;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
   t.dbg = tem_ablation_bits();

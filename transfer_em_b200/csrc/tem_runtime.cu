@@ -271,7 +271,8 @@ static int run_forward(const tem_handle* h, const LayerSpec& L, const float* net
   a.Cout = L.cout; a.slope = L.slope; a.drop_key = L.dropout ? drop_key : 0;
   a.use_lut = use_lut; a.lut_mean = mean; a.lut_std = stdv;
   if (stitched) *stitched = false;
-  if (stitch && h->cfg.use_tensor_cores && L.cout == 1 && C0 <= 32 && !getenv("TEM_NO_CONV_C1") && !getenv("TEM_NO_FUSED_STITCH") && conv_c1_supported(a)) {
+  if (stitch && h->cfg.use_tensor_cores && L.cout == 1 && C0 <= 32 && !getenv("TEM_NO_FUSED_STITCH") &&
+      ((!getenv("TEM_NO_CONV_TC") && tc_conv_supported(a)) || (!getenv("TEM_NO_CONV_C1") && conv_c1_supported(a)))) {
     // the single-channel last layer writes uint8 straight into the stitched volume (the fp32 tile output is never stored)
     a.st_out = stitch->out; a.st_index = stitch->index; a.st_tpad = stitch->tpad; a.st_od = stitch->od;
     a.st_mean = stitch->mean; a.st_std = stitch->stdv; a.st_OZ = stitch->OZ; a.st_OY = stitch->OY; a.st_OX = stitch->OX;
