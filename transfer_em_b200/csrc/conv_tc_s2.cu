@@ -95,7 +95,7 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
 
 // the same epilogue on a precomputed output pointer / dropout index (index arithmetic hoisted by the caller); LeakyReLU' of
 // the reference is taken from the raw bf16 halves: ref > 0 <=> sign bit clear and magnitude non-zero
-__device__ __forceinline__ uint4 epi_finish(const S2Args& a, float* v, const uint4& rq, const uint4& aq, bf16* op, uint32_t di) {
+__device__ __forceinline__ void epi_finish(const S2Args& a, float* v, const uint4& rq, const uint4& aq, bf16* op, uint32_t di) {
   if (a.ref) {
     const uint32_t w[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
@@ -119,12 +119,7 @@ __device__ __forceinline__ uint4 epi_finish(const S2Args& a, float* v, const uin
   }
   uint4 pk;
   pk.x = pack2(v[0], v[1]); pk.y = pack2(v[2], v[3]); pk.z = pack2(v[4], v[5]); pk.w = pack2(v[6], v[7]);
-  if (op && !(a.dbg & 32)) *reinterpret_cast<uint4*>(op) = pk;
-  return pk;
-}
-// 32 B store of two adjacent 16 B results (sm_100 256-bit store: full sectors instead of two half-sector writes)
-__device__ __forceinline__ void st256(bf16* op, const uint4& lo, const uint4& hi) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+  if (!(a.dbg & 32)) *reinterpret_cast<uint4*>(op) = pk;
 }
 
 __device__ __forceinline__ void decode_work(const S2Args& a, int& b, int& x0, int& y0, int& z0, int& nz) {
@@ -259,8 +254,6 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
     const bf16* const ref0 = a.ref ? a.ref + Epi::ref_off(a, b, oz0, oy0, ox0) : a.out;        // never read when a.ref == nullptr
     const uint32_t di0 = (uint32_t)(((((long long)b * a.L[0] + oz0) * a.L[1] + oy0) * a.L[2] + ox0) * a.Cout);
     const uint32_t di_zs = (uint32_t)(2 * a.L[1] * a.L[2] * a.Cout);
-    const bool pair8 = (ooff[1] - ooff[0]) == 8;          // 8-channel dense tensor: the two x-classes of a q-voxel are 32 contiguous bytes
-    uint4 pk_even = make_uint4(0, 0, 0, 0); bool ok_even = false;
     for (int zo = 0; zo < nz; ++zo) {
       const int oz = oz0 + 2 * zo;
       const bool zv = oz >= 0 && oz < a.L[0];
@@ -305,11 +298,6 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tempty_bar[zo & 1]);
         }
-        // Stores leave as 32 B where two 16 B results are adjacent in memory: the 16 channels of one voxel (CP >= 16), or, for
-        // 8-channel tensors, the two x-classes of a q-voxel (output voxels 2qx, 2qx+1; pad = 0 keeps the pair 32 B aligned).
-        // Measured before (stage ablation): this epilogue is half of g2.dgrad, and 16 B stores at a 32 B lane stride write
-        // every sector twice.
-        uint4 pk[NCH];
         if (ok) {
           const uint32_t di = di0 + (uint32_t)zo * di_zs + doff[c4];
 #pragma unroll
@@ -318,30 +306,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              pk[c] = epi_finish(a, v, refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c], nullptr, di + (uint32_t)(c * 8));
-            }
-          }
-        }
-        if (a.dbg & 32) continue;
-        if (NCH == 1) {
-          bf16* const op = outz + ooff[c4];
-          if ((c4 & 1) == 0) { pk_even = pk[0]; ok_even = ok; }
-          else {
-            bf16* const op0 = outz + ooff[c4 - 1];
-            if (ok_even && ok && pair8 && (reinterpret_cast<uintptr_t>(op0) & 31) == 0) st256(op0, pk_even, pk[0]);
-            else {
-              if (ok_even) *reinterpret_cast<uint4*>(op0) = pk_even;
-              if (ok) *reinterpret_cast<uint4*>(op) = pk[0];
-            }
-          }
-        } else if (ok) {
-          bf16* const op = outz + ooff[c4];
-#pragma unroll
-          for (int c = 0; c < NCH; c += 2) {
-            if (c * 8 + 8 < a.Cout && (reinterpret_cast<uintptr_t>(op + c * 8) & 31) == 0) st256(op + c * 8, pk[c], pk[c + 1]);
-            else {
-              if (c * 8 < a.Cout) *reinterpret_cast<uint4*>(op + c * 8) = pk[c];
-              if (c * 8 + 8 < a.Cout) *reinterpret_cast<uint4*>(op + c * 8 + 8) = pk[c + 1];
+              epi_finish(a, v, refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c], outz + ooff[c4] + c * 8, di + (uint32_t)(c * 8));
             }
           }
         }
