@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the transfer_em hot path on B200.
 
-Metric (BASELINE.json): 3D CycleGAN train voxels/s (+ tiled-inference Mvox/s as a secondary object).
-Workload at every N: BASELINE config 3 - EM2EM(74, is3d=True, wf=8) full train step (6 G + 4 D forward, combined
-backward, gradient all-reduce, Adam) on synthetic uint8 74^3 patches, per-GPU batch 8 (weak scaling).
+Metric (BASELINE.json): 3D CycleGAN train voxels/s & tiled-inference Mvox/s.
+Default line (every N): BASELINE config 3 - EM2EM(74, is3d=True, wf=8) full train step (6 G + 4 D forward, combined
+backward, gradient all-reduce, Adam) on synthetic uint8 74^3 patches, per-GPU batch 8 (weak scaling) - and, in the same
+line under "inference", BASELINE config 5: predict_ng_cube tiling of a 1024^3 request (24 389 tiles), z-slab sharded over
+the ranks, device-resident and end to end, with its own roofline and CPU per-tile arm.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
-  python bench.py --impl reference ...                     CPU arm: the reference's path on the host cores
+  python bench.py --config 4                               BASELINE config 4: wf = 1, 110^3 patches, batch 4 per GPU
+  python bench.py --config 5                               tiled inference as the headline line
+  python bench.py --impl reference [--config 5]            CPU arm: the reference's path on the host cores
 
 One JSON line is printed by rank 0.  train voxels/s = global_batch * 2 * 74^3 / step_time.
 """
@@ -233,7 +237,8 @@ def measure_inference(S, dev, rank, world, local, barrier, max_over_ranks, reps=
     from transfer_em_b200 import Engine
     nt = (S + 35) // 36
     V = nt * 36 + 38
-    ieng = Engine(dimsize=74, is3d=True, wf=WF, max_batch=64, train=False, device=local, seed=1234)
+    TB = 256                     # tiles per batch (measured, profiles/infer_layers_r2.txt: 64 -> 1520, 128 -> 1614, 256 -> 1657 Mvox/s on a 576^3 request)
+    ieng = Engine(dimsize=74, is3d=True, wf=WF, max_batch=TB, train=False, device=local, seed=1234)
     g = torch.Generator(device=dev); g.manual_seed(7)
     vol = torch.randint(0, 256, (V, V, V), dtype=torch.uint8, device=dev, generator=g)
     per, rem = divmod(nt, world)
@@ -279,7 +284,7 @@ def measure_inference(S, dev, rank, world, local, barrier, max_over_ranks, reps=
     res = {"metric": "tiled_inference_mvox_per_s", "value": S ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvox/s", "ms": ms,
            "request": f"{S}^3 of a uint8 {V}^3 source (seed 7), start (19,19,19), reference tiling: {tiles} tiles of 74^3 at stride 36, "
                       f"z tile-layers sharded over {world} GPU(s), no communication",
-           "tiles": tiles, "tiles_this_rank": my_tiles, "batch_tiles": 64, "gpu_launches": int(launches),
+           "tiles": tiles, "tiles_this_rank": my_tiles, "batch_tiles": TB, "gpu_launches": int(launches),
            "e2e": {"value": S ** 3 / (ms_e2e * 1e-3) / 1e6, "unit": "Mvox/s", "ms": ms_e2e, "h2d_bytes_per_step": int(h_src.numel()) * world,
                    "d2h_bytes_per_step": int(h_out.numel()) * world, "roundtrip_identical": ok},
            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": pk_src,
@@ -371,7 +376,7 @@ def main():
             emit({"metric": inf["metric"], "value": inf["value"], "unit": inf["unit"], "n_gpus": world, "steps": max(2, min(K, 5)), "warmup": 3,
                   "ms_per_step": inf["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                   "config": {"workload": "BASELINE config 5: " + inf["request"], "wf": WF, "parallelism": f"z-slab x{world}",
-                             "l2": "1.27 GB source + 1.07 GB output + 1.2 GB of per-batch activations >> 126 MB L2",
+                             "l2": "1.27 GB source + 1.07 GB output + 4.9 GB of per-batch activations >> 126 MB L2",
                              "warmup_note": "one full request is run before the timed ones (a request is thousands of launches)"},
                   "e2e": inf["e2e"], "gpu_launches": inf["gpu_launches"], "clocks": clocks, "roofline": inf["roofline"], "cpu_baseline": cpu})
         if world > 1:
