@@ -666,7 +666,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   tem_handle* h = new tem_handle();
   h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->keys_overridden = false; h->in_overlap = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
-  for (int i = 0; i < 4; ++i) h->aux[i] = nullptr; for (int i = 0; i < 12; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
+  for (int i = 0; i < 4; ++i) h->aux[i] = nullptr; for (int i = 0; i < 16; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
   h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
   h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
   long long off = 0;
@@ -700,7 +700,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
       for (int i = 0; i < 8; ++i) if ((rc = alloc_tensor(h, h->ddP[sset][i], DT_BF16, B, dd[i] > 0 ? dd[i] : 1, h->nets[2].L[i].cout))) return fail(rc);
     }
     for (int i = 0; i < 4; ++i) if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) { tem_set_error("stream create failed"); return fail(TEM_ERR_CUDA); }
-    for (int i = 0; i < 12; ++i) if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { tem_set_error("event create failed"); return fail(TEM_ERR_CUDA); }
+    for (int i = 0; i < 16; ++i) if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { tem_set_error("event create failed"); return fail(TEM_ERR_CUDA); }
     long long osz = (long long)B * h->outdim * h->outdim * (h->nd == 3 ? h->outdim : 1);
     for (int i = 0; i < 6; ++i) if ((rc = dev_alloc(h, (void**)&h->dOut[i], osz * 4))) return fail(rc);
     long long lsz = (long long)B * h->dl * h->dl * (h->nd == 3 ? h->dl : 1);
@@ -723,7 +723,7 @@ extern "C" int tem_destroy(tem_handle* h) {
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int i = 0; i < 4; ++i) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
-  for (int i = 0; i < 12; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 16; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);   // h_tile_index lives in the same allocation
   delete h;
@@ -930,14 +930,22 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   const int setB = overlap ? 1 : 0, setC = overlap ? 2 : 0, setD = overlap ? 3 : 0;
   h->in_overlap = overlap;
   if (overlap) {
-    // packed weight images are shared by all streams: refresh all of them before the fork
-    for (auto& kv : h->packed)
-      if (kv.second.version != h->params_version) {
-        TEM_CUDA(pack_tc_weights(kv.second.kind, kv.second.args, kv.second.buf, st));
-        kv.second.version = h->params_version;
-      }
     TEM_CUDA(cudaEventRecord(h->ev[0], st));
     for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
+    // Packed weight images are shared by all streams and stale after every Adam step: ~70 tiny pack launches (launch list of
+    // round 2: 0.2 ms when serialised in front of the fork).  They are spread round-robin over the four streams and every
+    // stream then waits for the packs of the other three.
+    int npk = 0;
+    for (auto& kv : h->packed)
+      if (kv.second.version != h->params_version) {
+        TEM_CUDA(pack_tc_weights(kv.second.kind, kv.second.args, kv.second.buf, ss[npk & 3]));
+        kv.second.version = h->params_version;
+        ++npk;
+      }
+    if (npk) {
+      for (int i = 0; i < 4; ++i) TEM_CUDA(cudaEventRecord(h->ev[12 + i], ss[i]));
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (i != j) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[12 + j], 0));
+    }
   }
   // ---- forward (pass ids: 0 fake_y, 1 cycled_x, 2 fake_x, 3 cycled_y, 4 same_x, 5 same_y)
   InputRef fy, fx;                                                                     // ZeroPadding3D(buffer): :161,:170

@@ -99,7 +99,7 @@ struct tem_handle {
   uint64_t params_version;
   // four internal streams overlap the independent passes of a train step (G(real_x) || F(real_y), ...)
   cudaStream_t aux[4];
-  cudaEvent_t ev[12];
+  cudaEvent_t ev[16];
   bool overlap_ready;
   bool in_overlap;              // a train step is between its stream fork and join
 };
