@@ -109,6 +109,12 @@ int tem_train_grads(tem_handle* h, const void* real_x, const void* real_y, int i
                     const float* meanstd_x, const float* meanstd_y, int B, float* losses_out, void* stream);
 /* Apply Adam to the current gradients (after tem_train_grads); grad_scale multiplies the gradients. */
 int tem_apply_adam(tem_handle* h, float grad_scale, void* stream);
+/* Measurement aid (not a training entry point): captures one train step (forward, backward, Adam; single GPU) into a CUDA
+ * graph and replays it `reps` times with the captured dropout keys / learning-rate scalar; writes the mean device time per
+ * replay.  tem_last_error() then holds "graph nodes: N".  Replaces nothing in the reference; used by tools/graph_probe.py. */
+int tem_debug_graph_replay(tem_handle* h, const void* real_x, const void* real_y, int in_dtype,
+                           const float* meanstd_x, const float* meanstd_y, int B, int reps, float* ms_per_step);
+
 /* Output of generator pass p of the last train step (0 fake_y,1 cycled_x,2 fake_x,3 cycled_y,4 same_x,5 same_y). */
 int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* count, void* stream);
 /* debug/test: gradient w.r.t. the pre-activation of layer `layer` left in the backward scratch by the LAST

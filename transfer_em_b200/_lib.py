@@ -54,6 +54,7 @@ _SIGS = {
     "tem_disc_forward": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "tem_disc_out_dim": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32)]),
     "tem_last_activation": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_int64), _P]),
+    "tem_debug_graph_replay": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "tem_train_step": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, _P, _P]),
     "tem_train_grads": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, _P, _P]),
     "tem_apply_adam": (C.c_int, [_P, C.c_float, _P]),

@@ -176,6 +176,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       int slot = 0; uint32_t ph = 0;
       for (int s = 0; s < nslices; ++s) {
         mbar_wait(&empty_bar[slot], ph ^ 1u);
+        if (a.dbg & 4) { mbar_arrive(&full_bar[slot]); if (++slot == RING) { slot = 0; ph ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)planes * SUB_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         for (int p = 0; p < planes; ++p)
@@ -204,7 +205,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           uint32_t acc = 0;
           uint32_t blo = wb16 | b_lbo;
 #pragma unroll
-          for (int mz = 0; mz < 2; ++mz) {
+          for (int mz = 0; mz < ((a.dbg & 16) ? 0 : 2); ++mz) {
             const uint32_t sb16 = (rbase + (uint32_t)(mz ? sl1 : zslot) * slot_bytes) >> 4;
 #pragma unroll
             for (int my = 0; my < 2; ++my) {
@@ -364,6 +365,7 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
       int slot = 0; uint32_t ph = 0;
       for (int s = 0; s < nslices; ++s) {
         mbar_wait(&empty_bar[slot], ph ^ 1u);
+        if (a.dbg & 4) { mbar_arrive(&full_bar[slot]); if (++slot == RING) { slot = 0; ph ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(4 * planes) * SUB_BYTES);
         uint8_t* dst = ring + (size_t)slot * slot_bytes;
         const int zin = 2 * z0 - a.pad + s + a.shift[0];
@@ -399,7 +401,7 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           uint32_t acc = 0;
           uint32_t blo = wb16 | b_lbo;
 #pragma unroll
-          for (int kz = 0; kz < 4; ++kz) {
+          for (int kz = 0; kz < ((a.dbg & 16) ? 0 : 4); ++kz) {
             int sl = zslot + kz; if (sl >= RING) sl -= RING;
             const uint32_t sb16 = (rbase + (uint32_t)sl * slot_bytes) >> 4;
 #pragma unroll

@@ -1072,6 +1072,41 @@ extern "C" int tem_train_step(tem_handle* h, const void* real_x, const void* rea
   return TEM_OK;
 }
 
+// Measurement aid: captures ONE train step (forward, backward, Adam; no all-reduce) into a CUDA graph and replays it `reps`
+// times.  The replays reuse the captured dropout keys and learning-rate scalar, so this is not a training entry point: it
+// answers "what would removing host launch overhead and inter-kernel launch gaps buy" before the step is made graph-safe.
+extern "C" int tem_debug_graph_replay(tem_handle* h, const void* real_x, const void* real_y, int in_dtype,
+                                      const float* msx, const float* msy, int B, int reps, float* ms_per_step) {
+  if (!h || !ms_per_step || reps < 1) ARG_FAIL("tem_debug_graph_replay: bad arguments");
+  if (h->comm) { tem_set_error("graph replay is a single-GPU measurement"); return TEM_ERR_STATE; }
+  cudaStream_t cs; TEM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {          // warm: packed-weight cache, function attributes, overlap path
+    TEM_CHECK(train_fwd_bwd(h, real_x, real_y, in_dtype, msx, msy, B, cs));
+    TEM_CHECK(apply_adam(h, 1.f, cs));
+  }
+  TEM_CUDA(cudaStreamSynchronize(cs));
+  cudaGraph_t graph; cudaGraphExec_t exec;
+  TEM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = train_fwd_bwd(h, real_x, real_y, in_dtype, msx, msy, B, cs);
+  if (rc == TEM_OK) rc = apply_adam(h, 1.f, cs);
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  if (rc != TEM_OK) return rc;
+  TEM_CUDA(e);
+  TEM_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) TEM_CUDA(cudaGraphLaunch(exec, cs));
+  TEM_CUDA(cudaEventRecord(e0, cs));
+  for (int i = 0; i < reps; ++i) TEM_CUDA(cudaGraphLaunch(exec, cs));
+  TEM_CUDA(cudaEventRecord(e1, cs));
+  TEM_CUDA(cudaStreamSynchronize(cs));
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_step = ms / reps;
+  size_t nodes = 0; cudaGraphGetNodes(graph, nullptr, &nodes);
+  tem_set_error("graph nodes: %zu", nodes);       // readable through tem_last_error() (not an error)
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(cs);
+  return TEM_OK;
+}
+
 extern "C" int tem_train_output(tem_handle* h, int pass, float* dst, int64_t* count, void* stream) {
   if (!h || pass < 0 || pass > 5 || !count) ARG_FAIL("bad arguments");
   if (!h->cfg.train || !h->gp[pass].valid) { tem_set_error("no train step has run"); return TEM_ERR_STATE; }
