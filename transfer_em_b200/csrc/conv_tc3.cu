@@ -46,6 +46,9 @@ struct Tc3Args {
   const bf16* ref; int RZ, RY, RX, ref_C, ref_coff, ref_off[3]; float ref_slope;
   uint32_t drop_key;
   int accumulate;
+  int split;                   // != 0: channels [split, Cout) go to out2 / ref2 (merged dgrad of a concat layer); dropout on [0, split)
+  bf16* out2; int O2Z, O2Y, O2X, out2_C, out2_off[3];
+  const bf16* ref2; int R2Z, R2Y, R2X, ref2_C, ref2_off[3]; float ref2_slope;
   int dbg;                     // stage-ablation bits (-DTEM_ABLATION builds only): 1 no epilogue work, 4 no input loads, 16 no MMAs
 };
 
@@ -54,7 +57,7 @@ __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
 }
 
-template <int CP>
+template <int CP, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 2)
 conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
   constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
@@ -211,6 +214,9 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     // far below what the ~2 us round trip needs (Little's law); PF slices ahead restore the bandwidth.
     constexpr int PF = 32 / CP >= 2 ? 32 / CP * 2 : 2;      // CP = 8: 8 slices, 16: 4, 32: 2  (32 registers)
     const long long ref_zstride = (long long)a.RY * a.RX * a.ref_C;
+    const long long ref2_zstride = (long long)a.R2Y * a.R2X * a.ref2_C;
+    const int split = SPLIT ? a.split : 64;                // 8-channel chunks at or above it belong to the second destination
+    const int drop_C = SPLIT ? a.split : a.Cout;
     uint64_t tf_ph = 0;                                      // phase bit of every tfull barrier (an item may use fewer steps)
     for (int it = blockIdx.x; it < a.items; it += gridDim.x) {
       int b, x0, y0, z0, nz; decode(it, b, x0, y0, z0, nz);
@@ -221,13 +227,21 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       // per-item bases: the per-slice part of every address is one multiply-add (index arithmetic hoisted out of the slice loop)
       const long long out_zstride = (long long)a.OY * a.OX * a.out_C;
       bf16* const out_base = a.out + ((((long long)b * a.OZ + z0 + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
-      const uint32_t di_base = (uint32_t)(((((long long)b * a.L[0] + z0) * a.L[1] + oy) * a.L[2] + ox) * a.Cout);
-      const uint32_t di_zstride = (uint32_t)(a.L[1] * a.L[2] * a.Cout);
+      const uint32_t di_base = (uint32_t)(((((long long)b * a.L[0] + z0) * a.L[1] + oy) * a.L[2] + ox) * drop_C);
+      const uint32_t di_zstride = (uint32_t)(a.L[1] * a.L[2] * drop_C);
       const long long ref_base = ((((long long)b * a.RZ + z0 + a.ref_off[0]) * a.RY + oy + a.ref_off[1]) * a.RX + ox + a.ref_off[2]) * a.ref_C + a.ref_coff;
+      // second destination (CP >= 16 only): bases carry -split so that chunk c sits at base + c there too
+      const long long out2_zstride = (long long)a.O2Y * a.O2X * a.out2_C;
+      bf16* const out2_base = SPLIT ? a.out2 + ((((long long)b * a.O2Z + z0 + a.out2_off[0]) * a.O2Y + oy + a.out2_off[1]) * a.O2X + ox + a.out2_off[2]) * a.out2_C - a.split : nullptr;
+      const long long ref2_base = !SPLIT ? 0 : ((((long long)b * a.R2Z + z0 + a.ref2_off[0]) * a.R2Y + oy + a.ref2_off[1]) * a.R2X + ox + a.ref2_off[2]) * a.ref2_C - a.split;
       auto fetch_ref = [&](int zo, uint4* qv) {
         if (a.ref && inside && zo < nz) {
 #pragma unroll
-          for (int c = 0; c < CP / 8; ++c) if (has_c8[c]) qv[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + ref_base + (long long)zo * ref_zstride + c * 8));
+          for (int c = 0; c < CP / 8; ++c) {
+            if (!has_c8[c]) continue;
+            const bf16* rp = (SPLIT && c * 8 >= split) ? a.ref2 + ref2_base + (long long)zo * ref2_zstride : a.ref + ref_base + (long long)zo * ref_zstride;
+            qv[c] = __ldg(reinterpret_cast<const uint4*>(rp + c * 8));
+          }
         }
       };
 #pragma unroll
@@ -260,8 +274,9 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
               if (c < a.Cout) {
                 float f[8];
                 unpack8(refq[pu][c / 8], f);
+                const float rs = (SPLIT && c >= split) ? a.ref2_slope : a.ref_slope;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
+                for (int u = 0; u < 8; ++u) v[c + u] *= (f[u] > 0.f) ? 1.f : rs;
               }
             }
           }
@@ -269,7 +284,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           if (a.drop_key) {
             const uint32_t di = di_base + (uint32_t)zo * di_zstride;
 #pragma unroll
-            for (int c = 0; c < CP; ++c) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
+            for (int c = 0; c < CP; ++c) if (!SPLIT || c < split) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
           }
           if (CP == 8 && a.out_f32) {           // g11 (16 -> 1, linear): one fp32 value per voxel, or the fused inference epilogue of utils.py:109-121
             const float y = a.slope != 1.f ? (v[0] > 0.f ? v[0] : v[0] * a.slope) : v[0];
@@ -285,10 +300,12 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             }
             continue;
           }
-          bf16* op = out_base + (long long)zo * out_zstride;
+          bf16* const op1 = out_base + (long long)zo * out_zstride;
+          bf16* const op2 = out2_base + (long long)zo * out2_zstride;
 #pragma unroll
           for (int c = 0; c < CP; c += 8) {
             if (c < a.Cout) {
+              bf16* const op = (SPLIT && c >= split) ? op2 : op1;
               float o[8];
               if (a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
               else {
@@ -381,6 +398,10 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (!last && (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8)) return false;
   if (a.st_out && !last) return false;
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
+  if (a.split) {     // two destinations: whole 8-channel chunks each, both bf16, both with a LeakyReLU' reference
+    if (last || a.split % 8 || a.split >= a.Cout || a.out_coff || a.ref_coff || !a.out2 || !a.ref || !a.ref2) return false;
+    if (a.out2_C % 8 || a.ref2_C % 8 || a.out_C % 8) return false;
+  }
   const size_t smem = ((tc3_packed_bytes(cin, a.Cout) + 1023) & ~(size_t)1023) + (size_t)2 * sb_of(cin == 8 ? 5 : 9 * (cin / 16)) * (cin / 8) * PLANE_STRIDE + 1024;   // two pipeline steps at least
   if (smem > 200 * 1024) return false;
   if (a.conv_off[0] || a.conv_off[1] || a.conv_off[2]) return false;
@@ -436,6 +457,9 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.st_OZ = a.st_OZ; t.st_OY = a.st_OY; t.st_OX = a.st_OX;
   t.ref = a.ref; t.RZ = a.RZ; t.RY = a.RY; t.RX = a.RX; t.ref_C = a.ref_C; t.ref_coff = a.ref_coff; t.ref_slope = a.ref_slope;
   t.drop_key = a.drop_key; t.accumulate = a.accumulate;
+  t.split = a.split; t.out2 = (bf16*)a.out2; t.O2Z = a.O2Z; t.O2Y = a.O2Y; t.O2X = a.O2X; t.out2_C = a.out2_C;
+  t.ref2 = a.ref2; t.R2Z = a.R2Z; t.R2Y = a.R2Y; t.R2X = a.R2X; t.ref2_C = a.ref2_C; t.ref2_slope = a.ref2_slope;
+  for (int i = 0; i < 3; ++i) { t.out2_off[i] = a.out2_off[i]; t.ref2_off[i] = a.ref2_off[i]; }
   t.dbg = tem_ablation_bits();
   CUtensorMap m0, m1;
   if (!tem_make_map_plane(&m0, &t.merged0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, HX, HY)) return cudaErrorInvalidValue;
@@ -460,13 +484,14 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.nbmax = (t.zc + 2 + sb - 1) / sb;
   if (t.nbmax > kMaxChunk) return cudaErrorInvalidConfiguration;
   const unsigned grid = (unsigned)(t.items < 2 * 148 ? t.items : 2 * 148);     // persistent: two CTAs per SM
-  static bool attr[3] = {false, false, false};
-#define LAUNCH_TC3(CPV, IDX)                                                                                            \
+  static bool attr[5] = {false, false, false, false, false};
+#define LAUNCH_TC3(CPV, SPL, IDX)                                                                                       \
   {                                                                                                                     \
-    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv3_tc3_kernel<CPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
-    conv3_tc3_kernel<CPV><<<grid, kTcThreads, smem, st>>>(m0, m1, t);                                                   \
+    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv3_tc3_kernel<CPV, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
+    conv3_tc3_kernel<CPV, SPL><<<grid, kTcThreads, smem, st>>>(m0, m1, t);                                              \
   }
-  if (cp == 8) LAUNCH_TC3(8, 0) else if (cp == 16) LAUNCH_TC3(16, 1) else LAUNCH_TC3(32, 2)
+  if (a.split) { if (cp == 16) LAUNCH_TC3(16, true, 3) else LAUNCH_TC3(32, true, 4) }
+  else if (cp == 8) LAUNCH_TC3(8, false, 0) else if (cp == 16) LAUNCH_TC3(16, false, 1) else LAUNCH_TC3(32, false, 2)
 #undef LAUNCH_TC3
   ++g_tem_launches;
   return cudaGetLastError();

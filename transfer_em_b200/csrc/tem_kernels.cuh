@@ -44,6 +44,11 @@ struct ConvArgs {
   float ref_slope;
   uint32_t drop_key;   // != 0: multiply by 2*keep(hash(idx ^ key)), idx = dense [B,L,Cout] index
   int accumulate;      // out += result
+  // merged data gradient of a crop-and-concat layer (generator.py:74-86 backwards): op-output channels [split, Cout) leave
+  // to a second tensor with its own window and LeakyReLU' reference; dropout (dense [B,L,split] index) covers [0, split)
+  // only.  split == 0: single destination.  Only the tcgen05 3x3x3 kernel implements it (tc_conv_supported)
+  int split; void* out2; int O2Z, O2Y, O2X, out2_C, out2_off[3];
+  const bf16* ref2; int R2Z, R2Y, R2X, ref2_C, ref2_off[3]; float ref2_slope;
   int use_lut; float lut_mean, lut_std;   // u8 input: (u/127.5 - 1 - mean)/std
   // fused inference epilogue of the Cout = 1 last generator layer (transfer_em/utils.py:109-121): un-standardise, crop tpad,
   // round-half-even, uint8 wrap, scatter tile b to its place in the stitched volume.  st_out == nullptr: plain output

@@ -331,6 +331,41 @@ static int run_dgrad(const tem_handle* h, const LayerSpec& L, const float* netp,
   return TEM_OK;
 }
 
+// merged data gradient of a crop-and-concat layer (generator.py:74-86 backwards): one pass over dy writes channels
+// [0, cu) of the input gradient to `out_up` (full extent, dropout, LeakyReLU' of a[up]) and channels [cu, cu+cs) to the
+// crop window of `out_skip` (LeakyReLU' of a[skip] at the same window).  Returns 1 when the shape is not covered by the
+// tcgen05 3x3x3 kernel (the caller then issues the two single-destination launches).
+static int run_dgrad_cat(const tem_handle* h, const LayerSpec& L, const float* netp, const Tensor& dy, int cu, int cs,
+                         const Tensor& out_up, const Tensor& ref_up, float slope_up, uint32_t drop_key,
+                         const Tensor& out_skip, const Tensor& ref_skip, float slope_skip, const int cropv[3],
+                         int B, cudaStream_t st) {
+  static const bool off = getenv("TEM_NO_DGRAD_CAT") != nullptr || getenv("TEM_NO_CONV_TC") != nullptr;   // debug knobs
+  if (off || L.transposed || !h->cfg.use_tensor_cores) return 1;
+  ConvArgs a; memset(&a, 0, sizeof(a));
+  a.s0 = view_of(dy); a.C0 = L.cout; a.C1 = 0;
+  layer_axes(h, L, a.k, a.stride, a.pad);
+  a.form = 1; a.ws_tap = (long long)L.cin * L.cout; a.ws_in = 1; a.ws_out = L.cout;
+  a.w = netp + L.w_off;
+  a.B = B;
+  for (int i = 0; i < 3; ++i) a.L[i] = out_up.d[i];
+  set_out(a, out_up, 0, nullptr);
+  a.Cout = cu + cs; a.slope = 1.0f; a.split = cu;
+  a.ref = (const bf16*)ref_up.p; a.RZ = ref_up.d[0]; a.RY = ref_up.d[1]; a.RX = ref_up.d[2]; a.ref_C = ref_up.C; a.ref_slope = slope_up;
+  a.out2 = out_skip.p; a.O2Z = out_skip.d[0]; a.O2Y = out_skip.d[1]; a.O2X = out_skip.d[2]; a.out2_C = out_skip.C;
+  a.ref2 = (const bf16*)ref_skip.p; a.R2Z = ref_skip.d[0]; a.R2Y = ref_skip.d[1]; a.R2X = ref_skip.d[2]; a.ref2_C = ref_skip.C; a.ref2_slope = slope_skip;
+  for (int i = 0; i < 3; ++i) { a.out2_off[i] = cropv[i]; a.ref2_off[i] = cropv[i]; }
+  a.drop_key = drop_key;
+  if (out_up.dtype != DT_BF16 || out_skip.dtype != DT_BF16 || ref_up.dtype != DT_BF16 || ref_skip.dtype != DT_BF16) return 1;
+  if (!tc_conv_supported(a)) return 1;
+  const double dvox = (double)B * dy.d[0] * dy.d[1] * dy.d[2];
+  const double xvox = (double)B * out_up.d[0] * out_up.d[1] * out_up.d[2];
+  const double bytes = dvox * L.cout * 2 + xvox * (cu + cs) * 4 + (double)L.w_count * 4;
+  const double macs = dvox * (cu + cs) * L.cout * 27.0;
+  ProfScope ps(h, L.name, "dgrad", bytes, 2 * macs, st);
+  TEM_CHECK(dispatch_conv(h, a, st));
+  return TEM_OK;
+}
+
 // weight gradient of layer L w.r.t. input channels [ci_off, ci_off+ci_cnt) taken from `x`
 static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const SrcView& x, int ci_off, int ci_cnt,
                      const Tensor& dy, int B, int use_lut, float mean, float stdv, cudaStream_t st) {
@@ -442,6 +477,8 @@ static int gen_backward(tem_handle* h, int net, GenPass& P, float* dout, float* 
     SrcView sv = view_of(P.a[skip]); for (int i = 0; i < 3; ++i) sv.shift[i] = cropv[i];
     TEM_CHECK(run_wgrad(h, L, g, sv, cu, cs, dP[li], B, 0, 0, 0, st));
     const uint32_t key = N.L[up].dropout ? (up == 6 ? P.keys[0] : P.keys[1]) : 0;
+    const int rc = run_dgrad_cat(h, L, w, dP[li], cu, cs, dP[up], P.a[up], N.L[up].slope, key, dP[skip], P.a[skip], N.L[skip].slope, cropv, B, st);
+    if (rc != 1) return rc;
     TEM_CHECK(run_dgrad(h, L, w, dP[li], 0, cu, dP[up], 0, nullptr, dP[up].d, nullptr, &P.a[up], nullptr, N.L[up].slope, key, 0, B, st));
     TEM_CHECK(run_dgrad(h, L, w, dP[li], cu, cs, dP[skip], 0, cropv, dP[up].d, nullptr, &P.a[skip], cropv, N.L[skip].slope, 0, 0, B, st));
     return TEM_OK;
