@@ -61,6 +61,8 @@ struct ConvArgs {
 struct WgradArgs {
   SrcView S;           // tensor read at s*p + k - pad
   int Ca;
+  SrcView S1; int Ca1; // Ca1 != 0: the last Ca1 of the Ca channels come from a second tensor (input of a crop-and-concat
+                       // layer, generator.py:74-86); only wgrad_tc.cu implements it
   const void* P; int p_dtype;
   int PZ, PY, PX, p_C, p_coff, p_off[3];
   long long p_bstride;

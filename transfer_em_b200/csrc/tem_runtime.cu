@@ -331,6 +331,33 @@ static int run_dgrad(const tem_handle* h, const LayerSpec& L, const float* netp,
   return TEM_OK;
 }
 
+// weight gradient of a crop-and-concat layer w.r.t. all its input channels in one pass over dy: rows [0, cu) of dw from
+// `xu`, rows [cu, cu+cs) from the window `xs`.  Returns 1 when wgrad_tc.cu does not cover the shape.
+static int run_wgrad_cat(const tem_handle* h, const LayerSpec& L, float* netg, const SrcView& xu, int cu, const SrcView& xs, int cs,
+                         const Tensor& dy, int B, cudaStream_t st) {
+  static const bool off = getenv("TEM_NO_WGRAD_CAT") != nullptr || getenv("TEM_NO_WGRAD_TC") != nullptr || getenv("TEM_NO_WGRAD_MMA") != nullptr;   // debug knobs
+  if (off || L.transposed || !h->cfg.use_tensor_cores) return 1;
+  WgradArgs a; memset(&a, 0, sizeof(a));
+  layer_axes(h, L, a.k, a.stride, a.pad);
+  a.B = B;
+  a.S = xu; a.S1 = xs; a.Ca = cu + cs; a.Ca1 = cs;
+  a.P = dy.p; a.p_dtype = dy.dtype; a.PZ = dy.d[0]; a.PY = dy.d[1]; a.PX = dy.d[2]; a.p_C = dy.C; a.p_coff = 0;
+  a.p_bstride = dy.per_sample(); a.Cb = L.cout;
+  for (int i = 0; i < 3; ++i) a.L[i] = dy.d[i];
+  a.dw = netg + L.w_off;
+  a.ws_tap = (long long)L.cin * L.cout; a.ws_a = L.cout; a.ws_b = 1;
+  if (!wgrad_tc_supported(a)) return 1;
+  const double dvox = (double)B * dy.d[0] * dy.d[1] * dy.d[2];
+  const double bytes = dvox * L.cout * 2 + (double)B * ((double)xu.Z * xu.Y * xu.X * cu + (double)(dy.d[0] + 2) * (dy.d[1] + 2) * (dy.d[2] + 2) * cs) * 2 + (double)L.w_count * 4;
+  const double macs = dvox * (cu + cs) * L.cout * 27.0;
+  ProfScope ps(h, L.name, "wgrad", bytes, 2 * macs, st);
+  const cudaError_t e = launch_wgrad_tc(a, st);
+  if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return 1; }
+  g_tem_last_kernel = "wgrad_tc_kernel";
+  TEM_CUDA(e);
+  return TEM_OK;
+}
+
 // merged data gradient of a crop-and-concat layer (generator.py:74-86 backwards): one pass over dy writes channels
 // [0, cu) of the input gradient to `out_up` (full extent, dropout, LeakyReLU' of a[up]) and channels [cu, cu+cs) to the
 // crop window of `out_skip` (LeakyReLU' of a[skip] at the same window).  Returns 1 when the shape is not covered by the
@@ -473,9 +500,13 @@ static int gen_backward(tem_handle* h, int net, GenPass& P, float* dout, float* 
   auto cat = [&](int li, int up, int skip, const int cropv[3]) -> int {   // layer li with input cat(a[up], crop(a[skip]))
     const LayerSpec& L = N.L[li];
     const int cu = N.L[up].cout, cs = N.L[skip].cout;
-    TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[up]), 0, cu, dP[li], B, 0, 0, 0, st));
     SrcView sv = view_of(P.a[skip]); for (int i = 0; i < 3; ++i) sv.shift[i] = cropv[i];
-    TEM_CHECK(run_wgrad(h, L, g, sv, cu, cs, dP[li], B, 0, 0, 0, st));
+    const int rw = run_wgrad_cat(h, L, g, view_of(P.a[up]), cu, sv, cs, dP[li], B, st);
+    if (rw < 0) return rw;
+    if (rw == 1) {
+      TEM_CHECK(run_wgrad(h, L, g, view_of(P.a[up]), 0, cu, dP[li], B, 0, 0, 0, st));
+      TEM_CHECK(run_wgrad(h, L, g, sv, cu, cs, dP[li], B, 0, 0, 0, st));
+    }
     const uint32_t key = N.L[up].dropout ? (up == 6 ? P.keys[0] : P.keys[1]) : 0;
     const int rc = run_dgrad_cat(h, L, w, dP[li], cu, cs, dP[up], P.a[up], N.L[up].slope, key, dP[skip], P.a[skip], N.L[skip].slope, cropv, B, st);
     if (rc != 1) return rc;

@@ -35,6 +35,8 @@ constexpr int kThreads = 192;
 struct WtArgs {
   int B, L[3];                 // extent of g (z,y,x)
   int pa, pb;                  // 8-channel planes of x / g
+  int pa0;                     // x planes [0, pa0) come from mapx, [pa0, pa) from mapx1 (two-source input of a concat layer)
+  int shift1[3];               // window shift of the second x tensor
   int RA, RB;                  // rows per plane in the x tile / in the g tile (RB = useful g rows per CTA)
   int M, N;                    // MMA shape: M = 8*pa*RA (64 or 128), N = 8*pb*RB
   int NR;                      // 16-voxel runs along x
@@ -57,7 +59,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const WtArgs a) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapx1, const __grid_constant__ CUtensorMap mapg, const WtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[XR_MAX], empty[XR_MAX], done_bar;
   const int NSLOT = a.XR, SB = a.sb;
@@ -111,8 +113,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
             for (int p = 0; p < a.pb; ++p)
               tma_load_5d(base + g_off + i * a.gb_bytes + p * gplane, &mapg, &full[slot], p * 8, -2, y0, zx0 + s0 + i - 2, b);
           for (int i = 0; i < nx; ++i)
-            for (int p = 0; p < a.pa; ++p)
-              tma_load_5d(base + i * a.xa_bytes + p * xplane, &mapx, &full[slot], p * 8, a.shift[2], y0 + a.shift[1], zx0 + s0 + i + a.shift[0], b);
+            for (int p = 0; p < a.pa; ++p) {
+              if (p < a.pa0) tma_load_5d(base + i * a.xa_bytes + p * xplane, &mapx, &full[slot], p * 8, a.shift[2], y0 + a.shift[1], zx0 + s0 + i + a.shift[0], b);
+              else tma_load_5d(base + i * a.xa_bytes + p * xplane, &mapx1, &full[slot], (p - a.pa0) * 8, a.shift1[2], y0 + a.shift1[1], zx0 + s0 + i + a.shift1[0], b);
+            }
           if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
       }
@@ -251,8 +255,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
 bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
   memset(&t, 0, sizeof(t));
   t.B = w.B; for (int i = 0; i < 3; ++i) { t.L[i] = w.L[i]; t.shift[i] = w.S.shift[i]; }
-  t.pa = w.Ca / 8; t.pb = w.Cb / 8;
-  t.M = (t.pa == 4) ? 128 : 64;
+  t.pa = w.Ca / 8; t.pb = w.Cb / 8; t.pa0 = (w.Ca - w.Ca1) / 8;
+  for (int i = 0; i < 3; ++i) t.shift1[i] = w.S1.shift[i];
+  t.M = (t.pa == 4 || (w.Ca1 && t.pa == 2 && w.Cb <= 16)) ? 128 : 64;     // two 8-channel sources: 8 x rows per plane, three g rows
   t.RA = (t.M / 8) / t.pa;
   int rb = t.RA - 2;
   static const char* nmax_s = getenv("TEM_WTC_NMAX");     // debug knob: 28 keeps the 9 accumulators within 256 TMEM columns
@@ -289,7 +294,11 @@ bool wgrad_tc_supported(const WgradArgs& w) {
   if (w.S.dtype != DT_BF16 || w.p_dtype != DT_BF16 || w.S.origins || w.use_lut) return false;
   for (int i = 0; i < 3; ++i) if (w.k[i] != 3 || w.stride[i] != 1 || w.pad[i] != 0 || w.p_off[i] != 0) return false;
   if (!(w.Ca == 8 || w.Ca == 16 || w.Ca == 32) || !(w.Cb == 8 || w.Cb == 16 || w.Cb == 32)) return false;
-  if (w.S.C != w.Ca || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
+  if (w.S.C != w.Ca - w.Ca1 || w.S.coff != 0 || w.p_C != w.Cb || w.p_coff != 0) return false;
+  if (w.Ca1) {
+    if (w.Ca1 % 8 || (w.Ca - w.Ca1) % 8 || w.Ca1 >= w.Ca || w.S1.dtype != DT_BF16 || w.S1.origins || w.S1.C != w.Ca1 || w.S1.coff != 0) return false;
+    if (w.S1.bstride != (long long)w.S1.Z * w.S1.Y * w.S1.X * w.S1.C) return false;
+  }
   if (w.PZ != w.L[0] || w.PY != w.L[1] || w.PX != w.L[2]) return false;      // OOB zero fill is the padding of g
   if (w.p_bstride != (long long)w.L[0] * w.L[1] * w.L[2] * w.Cb) return false;
   if (w.S.bstride != (long long)w.S.Z * w.S.Y * w.S.X * w.S.C) return false;
@@ -320,8 +329,10 @@ cudaError_t launch_wgrad_tc(const WgradArgs& w, cudaStream_t st) {
     if (eff > best_eff + 1e-9) { best_eff = eff; best = nzc; }
   }
   t.zc = (nslices + best - 1) / best; t.nzc = (nslices + t.zc - 1) / t.zc;
-  CUtensorMap mx, mg;
+  CUtensorMap mx, mx1, mg;
   if (!tem_make_map_5d(&mx, w.S.p, w.B, w.S.Z, w.S.Y, w.S.X, w.S.C, t.WA, t.RA)) return cudaErrorInvalidValue;
+  if (w.Ca1) { if (!tem_make_map_5d(&mx1, w.S1.p, w.B, w.S1.Z, w.S1.Y, w.S1.X, w.S1.C, t.WA, t.RA)) return cudaErrorInvalidValue; }
+  else mx1 = mx;
   if (!tem_make_map_5d(&mg, w.P, w.B, w.PZ, w.PY, w.PX, w.p_C, t.WB, t.RB)) return cudaErrorInvalidValue;
   static bool attr = false;
   if (!attr) { cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr = true; }
@@ -332,6 +343,6 @@ cudaError_t launch_wgrad_tc(const WgradArgs& w, cudaStream_t st) {
   long long want = mmas / (mpc_s ? atoi(mpc_s) : 96);
   if (want < 1) want = 1; if (want > 148) want = 148; if (want > t.units) want = t.units;
   const unsigned grid = (unsigned)want;
-  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mx, mg, t); ++g_tem_launches;
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(mx, mx1, mg, t); ++g_tem_launches;
   return cudaGetLastError();
 }
