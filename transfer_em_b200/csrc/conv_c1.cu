@@ -75,28 +75,28 @@ __global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const 
   }
   __syncthreads();
   const int lx = tid & 31, ly = tid >> 5;        // 32 x 8 threads, 4 voxels in z each
-  float acc[TZ][CO];
+  unsigned long long acc[TZ][CO / 2];              // channel pairs (FFMA2)
 #pragma unroll
   for (int j = 0; j < TZ; ++j)
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+    for (int c = 0; c < CO / 2; ++c) acc[j][c] = 0ull;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      float col[HZc];
+      unsigned long long col[HZc];                   // the input value in both halves
 #pragma unroll
-      for (int hz = 0; hz < HZc; ++hz) col[hz] = tile[(hz * HYc + ly + dy) * HXc + lx + dx];
+      for (int hz = 0; hz < HZc; ++hz) { const float t = tile[(hz * HYc + ly + dy) * HXc + lx + dx]; col[hz] = tem_pk2(t, t); }
 #pragma unroll
       for (int dz = 0; dz < 3; ++dz) {
         const float* wr = wsm + ((dz * 3 + dy) * 3 + dx) * CO;
-        float wv[CO];
+        unsigned long long wv[CO / 2];
 #pragma unroll
-        for (int c = 0; c < CO; c += 4) { const float4 w4 = *reinterpret_cast<const float4*>(wr + c); wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w; }
+        for (int c = 0; c < CO / 2; c += 2) { const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wr + 2 * c); wv[c] = w4.x; wv[c + 1] = w4.y; }
 #pragma unroll
         for (int j = 0; j < TZ; ++j)
 #pragma unroll
-          for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(col[j + dz], wv[c], acc[j][c]);
+          for (int c = 0; c < CO / 2; ++c) tem_ffma2(acc[j][c], col[j + dz], wv[c]);
       }
     }
   const int oy_ = y0 + ly, ox_ = x0 + lx;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const 
     if (oz_ >= a.L[0]) break;
     float v[CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) v[c] = acc[j][c];
+    for (int c = 0; c < CO / 2; ++c) tem_upk2(acc[j][c], v[2 * c], v[2 * c + 1]);
     if (a.ref) {
       const long long ro = ((((long long)b * a.RZ + oz_ + a.ref_off[0]) * a.RY + oy_ + a.ref_off[1]) * a.RX + ox_ + a.ref_off[2]) * a.ref_C + a.ref_coff;
 #pragma unroll
@@ -275,33 +275,33 @@ __global__ void __launch_bounds__(W2_NT, 3) conv_c1in_v2_kernel(const ConvArgs a
     }
     __syncthreads();
     if (tl + 1 < t1) w2_fetch<SDT>(a, tl + 1, ntx, nty, ntz, tid, raw);
-    float acc[W2_V][W2_TZ][8];
+    unsigned long long acc[W2_V][W2_TZ][4];          // channel pairs (FFMA2)
 #pragma unroll
     for (int v = 0; v < W2_V; ++v)
 #pragma unroll
       for (int j = 0; j < W2_TZ; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[v][j][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[v][j][c] = 0ull;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        float col[W2_V][W2_HZ];
+        unsigned long long col[W2_V][W2_HZ];         // the input value in both halves
 #pragma unroll
         for (int v = 0; v < W2_V; ++v)
 #pragma unroll
-          for (int hz = 0; hz < W2_HZ; ++hz) col[v][hz] = tile[(hz * W2_HY + ly + dy) * W2_HX + lx + 8 * v + dx];
+          for (int hz = 0; hz < W2_HZ; ++hz) { const float t = tile[(hz * W2_HY + ly + dy) * W2_HX + lx + 8 * v + dx]; col[v][hz] = tem_pk2(t, t); }
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8 + 4);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8);
+          const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wsm + ((dz * 3 + dy) * 3 + dx) * 8 + 4);
+          const unsigned long long wv[4] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
           for (int v = 0; v < W2_V; ++v)
 #pragma unroll
             for (int j = 0; j < W2_TZ; ++j)
 #pragma unroll
-              for (int c = 0; c < 8; ++c) acc[v][j][c] = fmaf(col[v][j + dz], wv[c], acc[v][j][c]);
+              for (int c = 0; c < 4; ++c) tem_ffma2(acc[v][j][c], col[v][j + dz], wv[c]);
         }
       }
     long long t = tl;
@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(W2_NT, 3) conv_c1in_v2_kernel(const ConvArgs a
           if (oz_ >= a.L[0]) break;
           float o[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { o[u] = acc[v][j][u]; if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope; }
+          for (int u = 0; u < 4; ++u) tem_upk2(acc[v][j][u], o[2 * u], o[2 * u + 1]);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope; }
           uint4 pk; pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
           bf16* op = reinterpret_cast<bf16*>(a.out) + ((((long long)b * a.OZ + oz_ + a.out_off[0]) * a.OY + oy_ + a.out_off[1]) * a.OX + ox_ + a.out_off[2]) * a.out_C + a.out_coff;
           *reinterpret_cast<uint4*>(op) = pk;

@@ -111,6 +111,17 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+// Packed fp32 FMA (sm_100: FFMA2).  A three-register FFMA issues every second cycle per scheduler on this part, the packed
+// form retires two FMAs in the same slot; each lane is an IEEE fma.rn, i.e. bit-identical to fmaf().
+__device__ __forceinline__ unsigned long long tem_pk2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void tem_upk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void tem_ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

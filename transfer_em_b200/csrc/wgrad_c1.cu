@@ -248,11 +248,11 @@ __global__ void __launch_bounds__(V2_NT, 3) wgrad_cin1_v2_kernel(const WgradArgs
   const int tid = threadIdx.x;
   if (SDT == DT_U8) for (int i = tid; i < 256; i += V2_NT) lut[i] = tem_standardize((float)i, a.lut_mean, a.lut_std);
   const int dz = blockIdx.y, cb0 = blockIdx.z * 8;
-  float acc[9][8];
+  unsigned long long acc2[9][4];                   // channel pairs (FFMA2)
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc2[t][c] = 0ull;
   const int lx = tid & (V2_LX - 1), ly = tid >> 3;
   const long long t0 = (long long)blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
   const bf16* Pp = reinterpret_cast<const bf16*>(a.P);
@@ -285,24 +285,33 @@ __global__ void __launch_bounds__(V2_NT, 3) wgrad_cin1_v2_kernel(const WgradArgs
 #pragma unroll
     for (int j = 0; j < V2_TZ; ++j) {
       if (j + 1 < V2_TZ) loadp(j + 1, pq[(j + 1) & 1]);
-      float pf[VPT][8];
+      unsigned long long pf[VPT][4];
 #pragma unroll
-      for (int v = 0; v < VPT; ++v) unpack8(pq[j & 1][v], pf[v]);
+      for (int v = 0; v < VPT; ++v) {
+        float f[8]; unpack8(pq[j & 1][v], f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pf[v][c] = tem_pk2(f[2 * c], f[2 * c + 1]);
+      }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const float* srow = &tile[(j * V2_HY + ly + r) * V2_HX + lx * VPT];
-        float sv[VPT + 2];
+        unsigned long long sv[VPT + 2];              // the input value in both halves
 #pragma unroll
-        for (int q = 0; q < VPT + 2; ++q) sv[q] = srow[q];
+        for (int q = 0; q < VPT + 2; ++q) { const float t = srow[q]; sv[q] = tem_pk2(t, t); }
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
           for (int v = 0; v < VPT; ++v)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[r * 3 + dx][c] = fmaf(sv[v + dx], pf[v][c], acc[r * 3 + dx][c]);
+            for (int c = 0; c < 4; ++c) tem_ffma2(acc2[r * 3 + dx][c], sv[v + dx], pf[v][c]);
       }
     }
   }
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tem_upk2(acc2[t][c], acc[t][2 * c], acc[t][2 * c + 1]);
   const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
