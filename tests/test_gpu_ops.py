@@ -446,7 +446,9 @@ def test_single_channel_conv_fast_paths():
     for tc in (1, 0):
         d = make_desc(B, dims, 1, 8, 3, 1, False, 0.3, 0, torch.uint8, torch.bfloat16, ms, tc=tc)
         y = conv_forward(torch.tensor(u).to(DEV), _cuda(w, torch.float32), d).float().cpu().numpy()
+        # tensor-core path (conv_c1tc.cu): the standardised input enters as a bf16 hi + lo pair, i.e. with ~16 mantissa bits
         np.testing.assert_allclose(y, naive.lrelu(naive.conv_fwd(xs, w, 1), 0.3), rtol=BF16_RTOL, atol=BF16_ATOL)
+        assert _lib.load().tem_last_kernel().decode() == ("conv_c1tc_kernel" if tc else "conv_direct_kernel")
     # C -> 1 forward (fp32 out) and its data gradient (1 -> C, flipped, pad 2, LeakyReLU' of the stored activation)
     x = bf16r(r.standard_normal((B,) + dims + (16,)))
     w1 = bf16r(r.standard_normal((3, 3, 3, 16, 1)) * 0.2)
@@ -457,6 +459,7 @@ def test_single_channel_conv_fast_paths():
     dy = r.standard_normal(ref.shape).astype(np.float32)
     act = bf16r(r.standard_normal(x.shape))
     dx = conv_dgrad(torch.tensor(dy).to(DEV), _cuda(w1, torch.float32), d, _cuda(act, torch.bfloat16), 0.3).float().cpu().numpy()
+    assert _lib.load().tem_last_kernel().decode() == "conv_c1tc_kernel"       # dy enters as a bf16 hi + lo pair
     dref = naive.conv_dgrad(dy.astype(np.float64), w1, 1, x.shape) * naive.lrelu_grad_from_output(act, 0.3)
     np.testing.assert_allclose(dx, dref, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 

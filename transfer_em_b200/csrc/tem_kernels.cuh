@@ -165,6 +165,13 @@ cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
 cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream_t st);
 const char* tc_s2_kernel_name(const ConvArgs& a);   // resident-weight or wide (streamed-weight) variant chosen for the shape
 
+// conv_c1tc.cu: tcgen05 kernel for the single-input-channel 3x3x3 layers (g0 / d0 forward, g11 data gradient): dx taps
+// folded into Toeplitz weight matrices
+bool c1tc_supported(const ConvArgs& a);
+size_t c1tc_packed_bytes(const ConvArgs& a);
+cudaError_t c1tc_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st);
+cudaError_t launch_conv_c1tc(const ConvArgs& a, const bf16* wimg, cudaStream_t st);
+
 // conv_small.cu: strided 4x4x4 forward for small output volumes with K = 64*Cin (d4, d6)
 bool conv_small_supported(const ConvArgs& a);
 cudaError_t launch_conv_small(const ConvArgs& a, cudaStream_t st);

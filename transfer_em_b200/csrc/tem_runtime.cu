@@ -181,11 +181,13 @@ static void set_out(ConvArgs& a, const Tensor& out, int coff, const int off[3]) 
 }
 
 static cudaError_t pack_tc_weights(int kind, const ConvArgs& a, bf16* dst, cudaStream_t st) {
+  if (kind == 4) return c1tc_pack_weights(a, dst, st);
   if (kind == 3) return tcw_pack_weights(a, dst, st);
   return kind == 2 ? tc_s2_pack_weights(a, dst, st) : tc3_pack_weights(a, dst, st);
 }
 static cudaError_t launch_tc_kind(int kind, const ConvArgs& a, const bf16* wp, cudaStream_t st) {
-  g_tem_last_kernel = kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? tc_s2_kernel_name(a) : "conv3_tc3_kernel";
+  g_tem_last_kernel = kind == 4 ? "conv_c1tc_kernel" : kind == 3 ? "conv3_tcw_kernel" : kind == 2 ? tc_s2_kernel_name(a) : "conv3_tc3_kernel";
+  if (kind == 4) return launch_conv_c1tc(a, wp, st);
   if (kind == 3) return launch_conv_tcw(a, wp, st);
   return kind == 2 ? launch_conv_tc_s2(a, wp, st) : launch_conv_tc3(a, wp, st);
 }
@@ -200,8 +202,9 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
   if (h->cfg.use_tensor_cores && !no_tc && tc_conv_supported(a)) kind = 0;
   else if (h->cfg.use_tensor_cores && !no_tc && tcw_conv_supported(a)) kind = 3;
   else if (h->cfg.use_tensor_cores && !no_tc && !no_s2 && tc_s2_supported(a)) kind = 2;
+  else if (h->cfg.use_tensor_cores && !no_tc && c1tc_supported(a)) kind = 4;
   if (kind >= 0) {
-    const size_t bytes = kind == 3 ? tcw_packed_bytes(a.C0 + a.C1, a.Cout) : kind == 2 ? tc_s2_packed_bytes(a) : tc3_packed_bytes(a.C0 + a.C1, a.Cout);
+    const size_t bytes = kind == 4 ? c1tc_packed_bytes(a) : kind == 3 ? tcw_packed_bytes(a.C0 + a.C1, a.Cout) : kind == 2 ? tc_s2_packed_bytes(a) : tc3_packed_bytes(a.C0 + a.C1, a.Cout);
     if (h->cfg.abi_version == 0) {         // throw-away handle of the per-op entry points: no cache
       bf16* tmp = nullptr;
       static bool pool_kept = false;       // keep freed blocks in the default pool across synchronisations
