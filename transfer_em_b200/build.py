@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtem_b200.so")
-SOURCES = ["tem_runtime.cu", "conv_direct.cu", "elementwise.cu", "wgrad_mma.cu", "wgrad_c1.cu", "conv_mma.cu", "conv_c1.cu", "conv_tc3.cu", "conv_tc_s2.cu", "wgrad_tc.cu", "conv_tcw.cu", "wgrad_tc_s2.cu", "conv_small.cu", "wgrad_tcw.cu", "disc_tail.cu", "conv_c1tc.cu"]
+SOURCES = ["tem_runtime.cu", "conv_direct.cu", "elementwise.cu", "wgrad_mma.cu", "wgrad_c1.cu", "conv_mma.cu", "conv_c1.cu", "conv_tc3.cu", "conv_tc_s2.cu", "wgrad_tc.cu", "conv_tcw.cu", "wgrad_tc_s2.cu", "conv_small.cu", "wgrad_tcw.cu", "disc_tail.cu", "conv_c1tc.cu", "wgrad_c1tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
 

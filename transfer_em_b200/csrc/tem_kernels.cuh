@@ -203,6 +203,10 @@ cudaError_t launch_wgrad_tcw(const WgradArgs& a, cudaStream_t st);
 // wgrad_c1.cu: weight gradient of the single-channel first / last layers
 bool wgrad_c1_supported(const WgradArgs& a);
 cudaError_t launch_wgrad_c1(const WgradArgs& a, cudaStream_t st);
+const char* wgrad_c1_last_name();     // "wgrad_c1_kernel" (CUDA cores) or "wgrad_c1tc_kernel" (tcgen05) for the last launch_wgrad_c1 call
+// wgrad_c1tc.cu: tcgen05 weight gradient of the single-channel layers (reached through launch_wgrad_c1)
+bool wgrad_c1tc_supported(const WgradArgs& w);
+cudaError_t launch_wgrad_c1tc(const WgradArgs& w, cudaStream_t st);
 
 // disc_tail.cu: fused tail of the 3-D discriminator (d5 .. d8: 64 -> 1 voxels per sample), one CTA per sample
 struct DiscTailArgs {

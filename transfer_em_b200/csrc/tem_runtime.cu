@@ -435,7 +435,7 @@ static int run_wgrad(const tem_handle* h, const LayerSpec& L, float* netg, const
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tc_s2_supported(a)) { e = launch_wgrad_tc_s2(a, st); g_tem_last_kernel = "wgrad_tc_s2_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && !no_wtc && wgrad_tcw_supported(a)) { e = launch_wgrad_tcw(a, st); g_tem_last_kernel = "wgrad_tcw_kernel"; }
     if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_mma && wgrad_mma_supported(a)) { e = launch_wgrad_mma(a, st); g_tem_last_kernel = "wgrad_mma_kernel"; }
-    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) { e = launch_wgrad_c1(a, st); g_tem_last_kernel = "wgrad_c1_kernel"; }
+    if (e == cudaErrorInvalidConfiguration && h->cfg.use_tensor_cores && !no_c1 && wgrad_c1_supported(a)) { e = launch_wgrad_c1(a, st); g_tem_last_kernel = wgrad_c1_last_name(); }
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_wgrad_direct(a, st); g_tem_last_kernel = "wgrad_direct_kernel"; }
     TEM_CUDA(e);
   }

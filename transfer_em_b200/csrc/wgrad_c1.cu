@@ -8,6 +8,7 @@
 #include "tem_kernels.cuh"
 
 extern unsigned long long g_tem_launches;
+static const char* g_wgrad_c1_name = "wgrad_c1_kernel";    // kernel family the last launch_wgrad_c1 call used
 
 namespace {
 
@@ -356,13 +357,19 @@ bool wgrad_c1_supported(const WgradArgs& w) {
   return false;
 }
 
+const char* wgrad_c1_last_name() { return g_wgrad_c1_name; }
+
 cudaError_t launch_wgrad_c1(const WgradArgs& w_in, cudaStream_t st) {
+  g_wgrad_c1_name = "wgrad_c1_kernel";
   WgradArgs a = w_in;
   a.nvox = (long long)a.B * a.L[0] * a.L[1] * a.L[2];
   if (a.nvox == 0) return cudaSuccess;
   static const bool old_c1 = getenv("TEM_WGRAD_C1_V1") != nullptr;   // debug knob: first-generation kernels
   if (!old_c1 && a.k[0] == 3) {
-    if (a.Ca == 1 && a.p_dtype == DT_BF16 && !a.S.origins && (a.use_lut ? a.S.dtype == DT_U8 : a.S.dtype != DT_U8)) return launch_cin1_v2(a, st);
+    if (a.Ca == 1 && a.p_dtype == DT_BF16 && !a.S.origins && (a.use_lut ? a.S.dtype == DT_U8 : a.S.dtype != DT_U8)) {
+      if (wgrad_c1tc_supported(a)) { g_wgrad_c1_name = "wgrad_c1tc_kernel"; return launch_wgrad_c1tc(a, st); }
+      return launch_cin1_v2(a, st);
+    }
     if (a.Cb == 1 && a.S.dtype == DT_BF16 && a.p_dtype != DT_U8 && a.p_C == 1 && a.p_coff == 0 && a.p_off[0] == 0 && a.p_off[1] == 0 &&
         a.p_off[2] == 0 && a.PZ == a.L[0] && a.PY == a.L[1] && a.PX == a.L[2]) {
       // dw[tap][ca] = sum_p S[p + tap][ca] P[p] = sum_u S[u][ca] P'[u + tap' - 2], tap' = 2 - tap: the single-channel
@@ -376,6 +383,7 @@ cudaError_t launch_wgrad_c1(const WgradArgs& w_in, cudaStream_t st) {
       s.B = a.B;
       s.dw = a.dw + 26 * a.ws_tap; s.ws_tap = -a.ws_tap; s.ws_a = 0; s.ws_b = a.ws_a;
       s.use_lut = 0;
+      if (wgrad_c1tc_supported(s)) { g_wgrad_c1_name = "wgrad_c1tc_kernel"; return launch_wgrad_c1tc(s, st); }
       return launch_cin1_v2(s, st);
     }
   }
