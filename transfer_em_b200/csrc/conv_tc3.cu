@@ -57,7 +57,10 @@ __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
 }
 
-template <int CP, bool SPLIT>
+// MODE selects the epilogue at compile time (a kernel that carries all of them is > 64 KB of code, which eight epilogue warps
+// per CTA fetch over and over): 0 forward (LeakyReLU), 1 data gradient (LeakyReLU' mask of `ref`, optional accumulate),
+// 2 data gradient with dropout, 3 Cout = 1 forward with fp32 / fused uint8 output (CP = 8)
+template <int CP, bool SPLIT, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Tc3Args a) {
   constexpr int NP = (CP == 8) ? 32 : 3 * CP;          // MMA N: three kz column groups (+ one zero group when CP == 8)
@@ -212,7 +215,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     // Operands of the fused epilogue (stored activation of the LeakyReLU' factor) are fetched PF output slices ahead of
     // their use: with one 16 B load per thread and slice in flight an SM keeps only ~4 KB of this stream outstanding,
     // far below what the ~2 us round trip needs (Little's law); PF slices ahead restore the bandwidth.
-    constexpr int PF = 32 / CP >= 2 ? 32 / CP * 2 : 2;      // CP = 8: 8 slices, 16: 4, 32: 2  (32 registers)
+    constexpr int PF = (MODE == 1 || MODE == 2) ? (32 / CP >= 2 ? 32 / CP * 2 : 2) : 1;      // CP = 8: 8 slices, 16: 4, 32: 2  (32 registers); forward: no operand to prefetch, one copy of the loop body
     const long long ref_zstride = (long long)a.RY * a.RX * a.ref_C;
     const long long ref2_zstride = (long long)a.R2Y * a.R2X * a.ref2_C;
     const int split = SPLIT ? a.split : 64;                // 8-channel chunks at or above it belong to the second destination
@@ -235,7 +238,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
       bf16* const out2_base = SPLIT ? a.out2 + ((((long long)b * a.O2Z + z0 + a.out2_off[0]) * a.O2Y + oy + a.out2_off[1]) * a.O2X + ox + a.out2_off[2]) * a.out2_C - a.split : nullptr;
       const long long ref2_base = !SPLIT ? 0 : ((((long long)b * a.R2Z + z0 + a.ref2_off[0]) * a.R2Y + oy + a.ref2_off[1]) * a.R2X + ox + a.ref2_off[2]) * a.ref2_C - a.split;
       auto fetch_ref = [&](int zo, uint4* qv) {
-        if (a.ref && inside && zo < nz) {
+        if ((MODE == 1 || MODE == 2) && a.ref && inside && zo < nz) {
 #pragma unroll
           for (int c = 0; c < CP / 8; ++c) {
             if (!has_c8[c]) continue;
@@ -268,7 +271,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
           float v[CP];
 #pragma unroll
           for (int c = 0; c < CP; ++c) v[c] = __uint_as_float(r[c]);
-          if (a.ref) {
+          if ((MODE == 1 || MODE == 2) && a.ref) {
 #pragma unroll
             for (int c = 0; c < CP; c += 8) {
               if (c < a.Cout) {
@@ -281,12 +284,12 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             }
           }
           fetch_ref(zo + 2 * PF, refq[pu]);
-          if (a.drop_key) {
+          if (MODE == 2 && a.drop_key) {
             const uint32_t di = di_base + (uint32_t)zo * di_zstride;
 #pragma unroll
             for (int c = 0; c < CP; ++c) if (!SPLIT || c < split) v[c] *= 2.f * tem_keep(a.drop_key, di + c);
           }
-          if (CP == 8 && a.out_f32) {           // g11 (16 -> 1, linear): one fp32 value per voxel, or the fused inference epilogue of utils.py:109-121
+          if (CP == 8 && MODE == 3) {           // g11 (16 -> 1, linear): one fp32 value per voxel, or the fused inference epilogue of utils.py:109-121
             const float y = a.slope != 1.f ? (v[0] > 0.f ? v[0] : v[0] * a.slope) : v[0];
             const int oz = z0 + zo;
             if (a.st_out) {
@@ -307,7 +310,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
             if (c < a.Cout) {
               bf16* const op = (SPLIT && c >= split) ? op2 : op1;
               float o[8];
-              if (a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
+              if (MODE >= 1 && a.accumulate) unpack8(*reinterpret_cast<const uint4*>(op + c), o);
               else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) o[u] = 0.f;
@@ -315,7 +318,7 @@ conv3_tc3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 o[u] += v[c + u];
-                if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
+                if (MODE == 0) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;      // slope = 1: identity
               }
               uint4 pk;
               pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
@@ -397,6 +400,7 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (a.C1 && (a.s1.dtype != DT_BF16 || a.s1.C % 8 || a.s1.coff != 0 || a.s1.C != a.C1)) return false;
   if (!last && (a.Cout % 8 || a.Cout > 32 || a.out_C % 8 || a.out_coff % 8)) return false;
   if (a.st_out && !last) return false;
+  if ((a.ref || a.drop_key || a.accumulate) && a.slope != 1.f) return false;     // the gradient epilogues carry no activation
   if (a.ref && (a.ref_C % 8 || a.ref_coff % 8)) return false;
   if (a.split) {     // two destinations: whole 8-channel chunks each, both bf16, both with a LeakyReLU' reference
     if (last || a.split % 8 || a.split >= a.Cout || a.out_coff || a.ref_coff || !a.out2 || !a.ref || !a.ref2) return false;
@@ -484,14 +488,21 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.nbmax = (t.zc + 2 + sb - 1) / sb;
   if (t.nbmax > kMaxChunk) return cudaErrorInvalidConfiguration;
   const unsigned grid = (unsigned)(t.items < 2 * 148 ? t.items : 2 * 148);     // persistent: two CTAs per SM
-  static bool attr[5] = {false, false, false, false, false};
-#define LAUNCH_TC3(CPV, SPL, IDX)                                                                                       \
+  static bool attr[14] = {};
+#define LAUNCH_TC3(CPV, SPL, MD, IDX)                                                                                   \
   {                                                                                                                     \
-    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv3_tc3_kernel<CPV, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
-    conv3_tc3_kernel<CPV, SPL><<<grid, kTcThreads, smem, st>>>(m0, m1, t);                                              \
+    if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv3_tc3_kernel<CPV, SPL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
+    conv3_tc3_kernel<CPV, SPL, MD><<<grid, kTcThreads, smem, st>>>(m0, m1, t);                                          \
   }
-  if (a.split) { if (cp == 16) LAUNCH_TC3(16, true, 3) else LAUNCH_TC3(32, true, 4) }
-  else if (cp == 8) LAUNCH_TC3(8, false, 0) else if (cp == 16) LAUNCH_TC3(16, false, 1) else LAUNCH_TC3(32, false, 2)
+#define LAUNCH_TC3_MODE(CPV, SPL, IDX)                                                                                  \
+  { if (mode == 2) LAUNCH_TC3(CPV, SPL, 2, IDX) else LAUNCH_TC3(CPV, SPL, 1, IDX + 1) }
+  // forward launches (no mask, no dropout, no accumulation, LeakyReLU or linear) take MODE 0; everything else the gradient modes
+  const int mode = t.out_f32 ? 3 : (a.drop_key ? 2 : ((a.ref || a.accumulate || a.split) ? 1 : 0));
+  if (a.split) { if (cp == 16) LAUNCH_TC3_MODE(16, true, 0) else LAUNCH_TC3_MODE(32, true, 2) }
+  else if (mode == 3) LAUNCH_TC3(8, false, 3, 4)
+  else if (mode == 0) { if (cp == 8) LAUNCH_TC3(8, false, 0, 5) else if (cp == 16) LAUNCH_TC3(16, false, 0, 6) else LAUNCH_TC3(32, false, 0, 7) }
+  else if (cp == 8) LAUNCH_TC3_MODE(8, false, 8) else if (cp == 16) LAUNCH_TC3_MODE(16, false, 10) else LAUNCH_TC3_MODE(32, false, 12)
+#undef LAUNCH_TC3_MODE
 #undef LAUNCH_TC3
   ++g_tem_launches;
   return cudaGetLastError();
