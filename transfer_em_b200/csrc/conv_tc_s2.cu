@@ -64,20 +64,23 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
   __device__ static __forceinline__ long long out_off(const S2Args& a, int b, int oz, int oy, int ox) {
     return ((((long long)b * a.OZ + oz + a.out_off[0]) * a.OY + oy + a.out_off[1]) * a.OX + ox + a.out_off[2]) * a.out_C + a.out_coff;
   }
+  // MODE (resident-weight kernels): 0 forward, 1 forward with dropout, 2 data gradient (LeakyReLU' mask, optional accumulate),
+  // 3 everything decided at run time.  Carrying all variants made conv_down_tc 110 KB of code for eight epilogue warps.
+  template <int MODE>
   __device__ static __forceinline__ void run(const S2Args& a, float* v, int c0, int b, int oz, int oy, int ox, const uint4& refq, const uint4& accq) {
-    if (a.ref) {
+    if (MODE >= 2 && a.ref) {
       float f[8];
       unpack8(refq, f);
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] *= (f[u] > 0.f) ? 1.f : a.ref_slope;
     }
-    if (a.drop_key) {
+    if ((MODE == 1 || MODE == 3) && a.drop_key) {
       const uint32_t di = (uint32_t)(((((long long)b * a.L[0] + oz) * a.L[1] + oy) * a.L[2] + ox) * a.Cout) + (uint32_t)c0;
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] *= 2.f * tem_keep(a.drop_key, di + u);
     }
     float o[8];
-    if (a.accumulate) unpack8(accq, o);
+    if (MODE >= 2 && a.accumulate) unpack8(accq, o);
     else {
 #pragma unroll
       for (int u = 0; u < 8; ++u) o[u] = 0.f;
@@ -85,7 +88,7 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       o[u] += v[u];
-      if (a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
+      if (MODE != 2 && a.slope != 1.f) o[u] = o[u] > 0.f ? o[u] : o[u] * a.slope;
     }
     uint4 pk;
     pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
@@ -95,8 +98,9 @@ struct Epi {   // fused epilogue on 8 channels of one output voxel; refq / accq:
 
 // the same epilogue on a precomputed output pointer / dropout index (index arithmetic hoisted by the caller); LeakyReLU' of
 // the reference is taken from the raw bf16 halves: ref > 0 <=> sign bit clear and magnitude non-zero
+template <int MODE>
 __device__ __forceinline__ void epi_finish(const S2Args& a, float* v, const uint4& rq, const uint4& aq, bf16* op, uint32_t di) {
-  if (a.ref) {
+  if (MODE >= 2 && a.ref) {
     const uint32_t w[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -104,16 +108,16 @@ __device__ __forceinline__ void epi_finish(const S2Args& a, float* v, const uint
       if (!((w[i] & 0x7fff0000u) != 0u && (w[i] & 0x80000000u) == 0u)) v[2 * i + 1] *= a.ref_slope;
     }
   }
-  if (a.drop_key) {
+  if ((MODE == 1 || MODE == 3) && a.drop_key) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] *= 2.f * tem_keep(a.drop_key, di + (uint32_t)u);
   }
-  if (a.accumulate) {
+  if (MODE >= 2 && a.accumulate) {
     float o[8]; unpack8(aq, o);
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] += o[u];
   }
-  if (a.slope != 1.f) {
+  if (MODE != 2 && a.slope != 1.f) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * a.slope;
   }
@@ -135,7 +139,7 @@ __device__ __forceinline__ void decode_work(const S2Args& a, int& b, int& x0, in
 // ------------------------------------------------------------------------------------------------
 // UP: NP = 8 * CP accumulator columns per q-slice (class-major), two TMEM stages
 // ------------------------------------------------------------------------------------------------
-template <int CP>
+template <int CP, int MODE>
 __global__ void __launch_bounds__(kThreadsUp)
 conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
   constexpr int NP = 8 * CP;
@@ -268,8 +272,8 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
               if (c * 8 < a.Cout) {
-                if (a.ref) refq[c4][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
-                if (a.accumulate) accq[c4][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
+                if (MODE >= 2 && a.ref) refq[c4][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
+                if (MODE >= 2 && a.accumulate) accq[c4][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
               }
             }
           }
@@ -286,8 +290,8 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             if (c * 8 < a.Cout) {
-              if (a.ref) refq[0][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
-              if (a.accumulate) accq[0][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
+              if (MODE >= 2 && a.ref) refq[0][c] = __ldg(reinterpret_cast<const uint4*>(refz + roff[c4] + c * 8));
+              if (MODE >= 2 && a.accumulate) accq[0][c] = *reinterpret_cast<const uint4*>(outz + ooff[c4] + c * 8);
             }
           }
         }
@@ -307,7 +311,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              epi_finish(a, v, refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c], outz + ooff[c4] + c * 8, di + (uint32_t)(c * 8));
+              epi_finish<MODE>(a, v, refq[kPrefetch ? c4 : 0][c], accq[kPrefetch ? c4 : 0][c], outz + ooff[c4] + c * 8, di + (uint32_t)(c * 8));
             }
           }
         }
@@ -325,7 +329,7 @@ conv_up_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 // ------------------------------------------------------------------------------------------------
 // DOWN: one ring slot = one input z-slice = 4 (ry,rx) de-interleaved sub-tiles x planes
 // ------------------------------------------------------------------------------------------------
-template <int NPAD>
+template <int NPAD, int MODE>
 __global__ void __launch_bounds__(kThreads)
 conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
   constexpr uint32_t kTmemCols = (2 * NPAD < 32) ? 32 : 2 * NPAD;
@@ -400,11 +404,13 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
         if (elect_one()) {
           uint32_t acc = 0;
           uint32_t blo = wb16 | b_lbo;
-#pragma unroll
+          // kz and the (ry, rx) class stay rolled: fully unrolled (32 bodies with both the Cin = 8 and the generic path) this loop
+          // alone was ~6000 instructions, i.e. the single issuing warp ran out of a 90 KB instruction footprint
+#pragma unroll 1
           for (int kz = 0; kz < ((a.dbg & 16) ? 0 : 4); ++kz) {
             int sl = zslot + kz; if (sl >= RING) sl -= RING;
             const uint32_t sb16 = (rbase + (uint32_t)sl * slot_bytes) >> 4;
-#pragma unroll
+#pragma unroll 1
             for (int rr = 0; rr < 4; ++rr) {
               const uint32_t tb16 = sb16 + (((uint32_t)(rr * planes) * SUB_STRIDE) >> 4);
 #pragma unroll
@@ -446,8 +452,8 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 #pragma unroll
         for (int c = 0; c < NPAD / 8; ++c) {
           if (c * 8 < a.Cout) {
-            if (a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + c * 8));
-            if (a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + c * 8);
+            if (MODE >= 2 && a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + c * 8));
+            if (MODE >= 2 && a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + c * 8);
           }
         }
       }
@@ -467,7 +473,7 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
           float v[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-          Epi::run(a, v, c * 8, b, oz, oy, ox, refq[c], accq[c]);
+          Epi::run<MODE>(a, v, c * 8, b, oz, oy, ox, refq[c], accq[c]);
         }
       }
     }
@@ -956,7 +962,7 @@ conv_downw_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
               float v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
-              Epi::run(a, v, co0 + cb + c * 8, b, oz, oy, ox, refq[c], accq[c]);
+              Epi::run<3>(a, v, co0 + cb + c * 8, b, oz, oy, ox, refq[c], accq[c]);
             }
           }
         }
@@ -1231,7 +1237,9 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   if (up) { if (!tem_make_map_plane(&m0, &t.merged, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, SXV, SYR)) return cudaErrorInvalidValue; }
   else if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)(cols * t.nzc);
-  static bool attr[5] = {false, false, false, false, false};
+  static bool attr[20] = {};
+  // epilogue variant (see Epi::run): plain forward, forward + dropout, data gradient, anything else
+  const int mode = (!a.ref && !a.accumulate) ? (a.drop_key ? 1 : 0) : ((!a.drop_key && a.slope == 1.f) ? 2 : 3);
 #define LAUNCH_S2(KERNEL, IDX)                                                                                          \
   {                                                                                                                     \
     if (!attr[IDX]) { cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr[IDX] = true; } \
@@ -1239,10 +1247,13 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
   }
   if (up) {
     const int cp = cp_of(a.Cout);
-    if (cp == 8) LAUNCH_S2(conv_up_tc_kernel<8>, 0) else if (cp == 16) LAUNCH_S2(conv_up_tc_kernel<16>, 1) else LAUNCH_S2(conv_up_tc_kernel<32>, 2)
+#define LAUNCH_S2_MODE(K, P, IDX)                                                                                       \
+  { if (mode == 0) LAUNCH_S2((K<P, 0>), IDX) else if (mode == 1) LAUNCH_S2((K<P, 1>), IDX + 1) else if (mode == 2) LAUNCH_S2((K<P, 2>), IDX + 2) else LAUNCH_S2((K<P, 3>), IDX + 3) }
+    if (cp == 8) LAUNCH_S2_MODE(conv_up_tc_kernel, 8, 0) else if (cp == 16) LAUNCH_S2_MODE(conv_up_tc_kernel, 16, 4) else LAUNCH_S2_MODE(conv_up_tc_kernel, 32, 8)
   } else {
-    if (npad_of(a.Cout) == 16) LAUNCH_S2(conv_down_tc_kernel<16>, 3) else LAUNCH_S2(conv_down_tc_kernel<32>, 4)
+    if (npad_of(a.Cout) == 16) LAUNCH_S2_MODE(conv_down_tc_kernel, 16, 12) else LAUNCH_S2_MODE(conv_down_tc_kernel, 32, 16)
   }
+#undef LAUNCH_S2_MODE
 #undef LAUNCH_S2
   ++g_tem_launches;
   return cudaGetLastError();
