@@ -158,11 +158,12 @@ wgrad_tc_s2_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_consta
   // ---- epilogue: 16 local taps (m'z, m'y, rx, m'x) x Ca x Cb image in shared memory, one atomic per weight and CTA
   float* red = reinterpret_cast<float*>(smem);
   const int Ca = a.pa * 8, Cb = a.pb * 8;
+  const int CbP = Cb + 4;                              // padded image rows: the float4 read-modify-writes of 8 consecutive ca fall into different bank groups
   const int nred = 16 * Ca * Cb;
   if (warp >= 2) {
     mbar_wait(&done_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int i = threadIdx.x - 64; i < nred; i += 128) red[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < 16 * Ca * CbP; i += 128) red[i] = 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int q = warp & 3;
     const int m = (a.M == 128) ? q * 32 + lane : q * 16 + (lane & 15);
@@ -174,30 +175,47 @@ wgrad_tc_s2_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_consta
       const bool use = rowok && my >= 0 && my < 2;
       for (int acc = 0; acc < 8; ++acc) {
         const int rx = acc >> 2, mz = (acc >> 1) & 1, mx = acc & 1;
-        for (int pB = 0; pB < a.pb; ++pB) {
-          uint32_t r[8];
+        float* const rowp = red + ((size_t)(((mz * 2 + my) * 2 + rx) * 2 + mx) * Ca + ca) * CbP;
+        for (int pB = 0; pB < a.pb; pB += 2) {              // two 8-column loads in flight per wait
+          uint32_t r[16];
           tmem_ld8(lane_base + (uint32_t)(acc * a.N + (pB * a.RB + j) * 8), r);
+          if (pB + 1 < a.pb) tmem_ld8(lane_base + (uint32_t)(acc * a.N + ((pB + 1) * a.RB + j) * 8), r + 8);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (use) {
-            float4* dst = reinterpret_cast<float4*>(red + ((size_t)(((mz * 2 + my) * 2 + rx) * 2 + mx) * Ca + ca) * Cb + pB * 8);
-            float4 v0 = dst[0], v1 = dst[1];
-            v0.x += __uint_as_float(r[0]); v0.y += __uint_as_float(r[1]); v0.z += __uint_as_float(r[2]); v0.w += __uint_as_float(r[3]);
-            v1.x += __uint_as_float(r[4]); v1.y += __uint_as_float(r[5]); v1.z += __uint_as_float(r[6]); v1.w += __uint_as_float(r[7]);
-            dst[0] = v0; dst[1] = v1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (pB + h < a.pb) {
+                float4* dst = reinterpret_cast<float4*>(rowp + (pB + h) * 8);
+                float4 v0 = dst[0], v1 = dst[1];
+                v0.x += __uint_as_float(r[8 * h + 0]); v0.y += __uint_as_float(r[8 * h + 1]); v0.z += __uint_as_float(r[8 * h + 2]); v0.w += __uint_as_float(r[8 * h + 3]);
+                v1.x += __uint_as_float(r[8 * h + 4]); v1.y += __uint_as_float(r[8 * h + 5]); v1.z += __uint_as_float(r[8 * h + 6]); v1.w += __uint_as_float(r[8 * h + 7]);
+                dst[0] = v0; dst[1] = v1;
+              }
+            }
           }
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    const int rot = (int)(((long long)blockIdx.x * nred / gridDim.x) & ~127LL);
-    for (int i0 = threadIdx.x - 64; i0 < nred; i0 += 128) {
-      int i = i0 + rot; if (i >= nred) i -= nred;
-      const float v = red[i];
-      if (v != 0.f) {
-        const int cb = i % Cb; int t = i / Cb; const int cA = t % Ca; t /= Ca;
+    // one vector reduction per four weights and CTA (Ca, Cb are powers of two: shifts instead of divisions); every CTA starts
+    // its pass at a different offset (fewer same-address collisions in L2)
+    const int lg_cb4 = (Cb == 8) ? 1 : (Cb == 16 ? 2 : 3), lg_ca = (Ca == 8) ? 3 : (Ca == 16 ? 4 : 5);
+    const int n4 = nred >> 2;
+    const bool vec4 = a.ws_b == 1 && (reinterpret_cast<uintptr_t>(a.dw) & 15) == 0 && (a.ws_tap & 3) == 0 && (a.ws_a & 3) == 0;
+    const int rot = (int)(((long long)blockIdx.x * n4 / gridDim.x) & ~127LL);
+    for (int i0 = threadIdx.x - 64; i0 < n4; i0 += 128) {
+      int i = i0 + rot; if (i >= n4) i -= n4;
+      const float4 v = *reinterpret_cast<const float4*>(red + (size_t)(i >> lg_cb4) * CbP + (i & ((1 << lg_cb4) - 1)) * 4);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+        const int c4 = i & ((1 << lg_cb4) - 1); int t = i >> lg_cb4; const int cA = t & (Ca - 1); t >>= lg_ca;
         const int mx = t & 1, rx = (t >> 1) & 1, my = (t >> 2) & 1, mz = t >> 3;
         const int kz = 2 * (mlz + mz) + rz + a.pad, ky = 2 * (mly + my) + ry + a.pad, kx = 2 * (mlo_of(rx, a.pad) + mx) + rx + a.pad;
-        atomicAdd(a.dw + (long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)cA * a.ws_a + (long long)cb * a.ws_b, v);
+        float* dst = a.dw + (long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)cA * a.ws_a + (long long)(c4 * 4) * a.ws_b;
+        if (vec4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        } else {
+          atomicAdd(dst, v.x); atomicAdd(dst + a.ws_b, v.y); atomicAdd(dst + 2 * a.ws_b, v.z); atomicAdd(dst + 3 * a.ws_b, v.w);
+        }
       }
     }
   }
@@ -230,7 +248,7 @@ bool plan(const WgradArgs& w, WsArgs& t, size_t& smem) {
   t.XR = 2; t.DR = 4;
   while (t.XR < XR_MAX && (size_t)(t.XR + 1) * 2 * t.xa_bytes + (size_t)(t.DR + 1) * t.gb_bytes <= 150 * 1024) { ++t.XR; ++t.DR; }
   smem = (size_t)t.XR * 2 * t.xa_bytes + (size_t)t.DR * t.gb_bytes + 1024;
-  const size_t red = (size_t)16 * w.Ca * w.Cb * 4;
+  const size_t red = (size_t)16 * w.Ca * (w.Cb + 4) * 4;
   if (red + 1024 > smem) smem = red + 1024;
   return smem <= 200 * 1024;
 }
