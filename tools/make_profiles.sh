@@ -24,8 +24,11 @@ cap g7_wgrad_tc g7.wgrad wgrad_tc_kernel
 cap g2_dgrad_conv_up g2.dgrad conv_up_tc
 cap g2_fwd_conv_down g2.fwd conv_down_tc
 cap g2_wgrad_tc_s2 g2.wgrad wgrad_tc_s2
-cap g0_wgrad_cin1_v2 g0.wgrad wgrad_cin1_v2
-cap g0_fwd_conv_c1 g0.fwd conv_c1in
+cap g0_wgrad_c1tc g0.wgrad wgrad_c1tc
+cap g0_fwd_conv_c1tc g0.fwd conv_c1tc
+cap g11_dgrad_conv_c1tc g11.dgrad conv_c1tc
+cap g1_dgrad_conv3_tc3 g1.dgrad conv3_tc3
+cap g6_wgrad_tc_s2 g6.wgrad wgrad_tc_s2
 cap g11_fwd_conv3_tc3 g11.fwd conv3_tc3
 cap w1_fwd_conv3_tcw w1.fwd conv3_tcw B=4
 cap w7_fwd_conv3_tcw w7.fwd conv3_tcw B=4
