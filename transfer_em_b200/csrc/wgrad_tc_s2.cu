@@ -276,7 +276,7 @@ bool wgrad_tc_s2_supported(const WgradArgs& w) {
   if (w.p_bstride != (long long)w.L[0] * w.L[1] * w.L[2] * w.Cb) return false;
   if (w.S.bstride != (long long)w.S.Z * w.S.Y * w.S.X * w.S.C) return false;
   static const char* mv_s = getenv("TEM_WS2_MINVOX");          // debug knob
-  if ((long long)w.L[0] * w.L[1] * w.L[2] < (mv_s ? atoi(mv_s) : 512)) return false;     // tiny volumes (d4, d6): the per-CTA epilogue outweighs the MMAs
+  if ((long long)w.L[0] * w.L[1] * w.L[2] < (mv_s ? atoi(mv_s) : 128)) return false;     // one-voxel layers (d6): the per-CTA epilogue outweighs the MMAs; d4 (6^3) is 26 us here against 45 us on wgrad_mma since the epilogue leaves as red.v4
   WsArgs t; size_t smem;
   if (!plan(w, t, smem)) return false;
   return tem_get_encode() != nullptr;
