@@ -451,7 +451,9 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   int nzc = (a.L[0] + t.zcap - 1) / t.zcap;
   static const char* mc_s = getenv("TEM_TC3_MINCHUNK");
   const int min_chunk = mc_s ? atoi(mc_s) : 3;     // measured: small layers are a serial MMA chain per CTA, finer z chunks spread it over more SMs
-  while (cols * nzc < 2 * 148 && (a.L[0] + nzc) / (nzc + 1) >= min_chunk) ++nzc;
+  static const char* r32_s = getenv("TEM_TC3_RES32");          // debug knob
+  const int resident = 148 * ((t.tmem_cols == 512) ? (r32_s ? atoi(r32_s) : 1) : 2);     // CTAs the GPU holds at once: a 512-column strip takes the whole TMEM of an SM
+  while (cols * nzc < resident && (a.L[0] + nzc) / (nzc + 1) >= min_chunk) ++nzc;
   t.zc = (a.L[0] + nzc - 1) / nzc; t.nzc = (a.L[0] + t.zc - 1) / t.zc;
   t.out = (bf16*)a.out; t.OZ = a.OZ; t.OY = a.OY; t.OX = a.OX; t.out_C = a.out_C; t.out_coff = a.out_coff;
   for (int i = 0; i < 3; ++i) { t.out_off[i] = a.out_off[i]; t.ref_off[i] = a.ref_off[i]; }
@@ -487,7 +489,7 @@ cudaError_t launch_conv_tc3(const ConvArgs& a, const bf16* wpacked, cudaStream_t
   t.items = (int)(cols * t.nzc);
   t.nbmax = (t.zc + 2 + sb - 1) / sb;
   if (t.nbmax > kMaxChunk) return cudaErrorInvalidConfiguration;
-  const unsigned grid = (unsigned)(t.items < 2 * 148 ? t.items : 2 * 148);     // persistent: two CTAs per SM
+  const unsigned grid = (unsigned)(t.items < resident ? t.items : resident);     // persistent: every CTA resident from the start
   static bool attr[14] = {};
 #define LAUNCH_TC3(CPV, SPL, MD, IDX)                                                                                   \
   {                                                                                                                     \
