@@ -1026,20 +1026,10 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   InputRef fyd, fxd;
   TEM_CHECK(make_input(h, gp[0].a[11].p, DT_F32, od, 0, nullptr, fyd));
   TEM_CHECK(make_input(h, gp[2].a[11].p, DT_F32, od, 0, nullptr, fxd));
-  TEM_CHECK(gen_forward(h, G, gp[0], rx, B, n, keys + 0, sA));                         // cgan.py:152
-  TEM_CHECK(gen_forward(h, F, gp[2], ry, B, n, keys + 4, sB));                         // :167
-  TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, sC));                         // :177
-  TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, sD));                        // :181
-  TEM_CHECK(gen_forward(h, F, gp[1], fy, B, n, keys + 2, sA));                         // :162
-  TEM_CHECK(gen_forward(h, G, gp[3], fx, B, n, keys + 6, sB));                         // :171
-  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sC));                               // :185
-  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sD));                               // :186
-  TEM_CHECK(disc_forward(h, DX, dp[2], fxd, B, od, sB));                               // :188 (fake_x lives on stream B)
-  TEM_CHECK(disc_forward(h, DY, dp[3], fyd, B, od, sA));                               // :189 (fake_y lives on stream A)
-  if (overlap) {
-    for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[1 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[1 + i], 0)); }
-  }
-  // ---- losses (accumulators live behind the gradient arena so one all-reduce covers both)
+  // Every stream carries its passes from forward through loss to backward without a global join: C / D (identity pass +
+  // the discriminator on the reals) are half as long as A / B (two chained generator passes + the discriminator on the
+  // fake) in the forward phase and start their backward while A / B are still in their second forward pass.  Cross-stream
+  // edges: the disc-loss backward of D_x(fake_x) on C needs B's forward of it (ev[1]), D_y(fake_y) on D needs A's (ev[2]).
   float* LS = h->loss_dev;
   const long long nl = (long long)B * dp[0].a[8].per_sample();
   const bool focal = h->cfg.loss_mode == TEM_LOSS_FOCAL;
@@ -1049,38 +1039,48 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   const float s_cyc = focal ? 4.f : 1.f, s_id = focal ? 2.f : 0.5f;
   const float* lg_dxr = (const float*)dp[0].a[8].p; const float* lg_dyr = (const float*)dp[1].a[8].p;
   const float* lg_dxf = (const float*)dp[2].a[8].p; const float* lg_dyf = (const float*)dp[3].a[8].p;
-  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 1.f, gamma, s_gen, lm, LS + 4, h->dlog[0], st));    // gen_g  :192
-  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 1.f, gamma, s_gen, lm, LS + 5, h->dlog[1], st));    // gen_f  :193
-  TEM_CUDA(launch_focal_logits(lg_dyr, nl, 1.f, gamma, s_disc, lm, LS + 2, h->dlog[2], st));   // disc_y :203
-  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 0.f, gamma, s_disc, lm, LS + 2, h->dlog[3], st));
-  TEM_CUDA(launch_focal_logits(lg_dxr, nl, 1.f, gamma, s_disc, lm, LS + 3, h->dlog[4], st));   // disc_x :202
-  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 0.f, gamma, s_disc, lm, LS + 3, h->dlog[5], st));
-  TEM_CHECK(pair_loss(h, rx, (const float*)gp[1].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[1], st));   // cycle x :196
-  TEM_CHECK(pair_loss(h, ry, (const float*)gp[3].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[3], st));   // cycle y
-  TEM_CHECK(pair_loss(h, rx, (const float*)gp[4].a[11].p, B, 0, s_id, LS + 8, h->dOut[4], st));      // identity f :200
-  TEM_CHECK(pair_loss(h, ry, (const float*)gp[5].a[11].p, B, 0, s_id, LS + 7, h->dOut[5], st));      // identity g :199
-  if (overlap) {
-    TEM_CUDA(cudaEventRecord(h->ev[5], st));
-    for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[5], 0));
-  }
-  // ---- backward.  Stream A owns fake_y's gradient (dOut[0]), stream B fake_x's (dOut[2]); C and D take the
-  // discriminators' own gradients and the identity passes.
+  // debug knob: TEM_DEBUG_GEN_BWD=k runs only the first k generator backward passes (scratch then holds pass k)
+  const int lim = lim_s ? atoi(lim_s) : 6;
+  // ---- forward
+  TEM_CHECK(gen_forward(h, G, gp[0], rx, B, n, keys + 0, sA));                         // cgan.py:152
+  TEM_CHECK(gen_forward(h, F, gp[2], ry, B, n, keys + 4, sB));                         // :167
+  TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, sC));                         // :177
+  TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, sD));                        // :181
+  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sC));                               // :185
+  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sD));                               // :186
+  TEM_CHECK(gen_forward(h, F, gp[1], fy, B, n, keys + 2, sA));                         // :162
+  TEM_CHECK(gen_forward(h, G, gp[3], fx, B, n, keys + 6, sB));                         // :171
+  TEM_CHECK(disc_forward(h, DX, dp[2], fxd, B, od, sB));                               // :188 (fake_x lives on stream B)
+  TEM_CHECK(disc_forward(h, DY, dp[3], fyd, B, od, sA));                               // :189 (fake_y lives on stream A)
+  if (overlap) { TEM_CUDA(cudaEventRecord(h->ev[1], sB)); TEM_CUDA(cudaEventRecord(h->ev[2], sA)); }
+  // ---- streams C / D: identity loss + the discriminator loss on the reals, their backward passes
+  // (loss accumulators live behind the gradient arena so one all-reduce covers both)
+  TEM_CHECK(pair_loss(h, rx, (const float*)gp[4].a[11].p, B, 0, s_id, LS + 8, h->dOut[4], sC));      // identity f :200
+  TEM_CUDA(launch_focal_logits(lg_dxr, nl, 1.f, gamma, s_disc, lm, LS + 3, h->dlog[4], sC));         // disc_x :202
+  TEM_CHECK(pair_loss(h, ry, (const float*)gp[5].a[11].p, B, 0, s_id, LS + 7, h->dOut[5], sD));      // identity g :199
+  TEM_CUDA(launch_focal_logits(lg_dyr, nl, 1.f, gamma, s_disc, lm, LS + 2, h->dlog[2], sD));         // disc_y :203
+  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sC, setC));       // disc_x wrt D_x   :212
+  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sD, setD));       // disc_y wrt D_y   :214
+  if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, sC, setC));
+  if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, sD, setD));
+  // ---- streams A / B: generator loss through the discriminator on the fake, cycle loss, their backward passes.  Stream A
+  // owns fake_y's gradient (dOut[0]), stream B fake_x's (dOut[2])
+  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 1.f, gamma, s_gen, lm, LS + 4, h->dlog[0], sA));          // gen_g  :192
+  TEM_CHECK(pair_loss(h, rx, (const float*)gp[1].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[1], sA));   // cycle x :196
+  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 1.f, gamma, s_gen, lm, LS + 5, h->dlog[1], sB));          // gen_f  :193
+  TEM_CHECK(pair_loss(h, ry, (const float*)gp[3].a[11].p, B, buf, s_cyc, LS + 6, h->dOut[3], sB));   // cycle y
   TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[0], false, h->dOut[0], sA, 0));      // d gen_g / d fake_y
   TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[1], false, h->dOut[2], sB, setB));   // d gen_f / d fake_x
-  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sC, setC));       // disc_y wrt D_y   :214
-  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sD, setD));       // disc_x wrt D_x   :212
-  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sC, setC));
-  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sD, setD));
-  {
-    // debug knob: TEM_DEBUG_GEN_BWD=k runs only the first k generator backward passes (scratch then holds pass k)
-    const int lim = lim_s ? atoi(lim_s) : 6;
-    if (lim > 0) TEM_CHECK(gen_backward(h, F, gp[1], h->dOut[1], h->dOut[0], sA, 0));         // cycled_x -> F, and into fake_y
-    if (lim > 1) TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], sB, setB));      // cycled_y -> G, and into fake_x
-    if (lim > 2) TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, sA, 0));
-    if (lim > 3) TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, sB, setB));
-    if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, sC, setC));
-    if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, sD, setD));
-  }
+  if (lim > 0) TEM_CHECK(gen_backward(h, F, gp[1], h->dOut[1], h->dOut[0], sA, 0));         // cycled_x -> F, and into fake_y
+  if (lim > 1) TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], sB, setB));      // cycled_y -> G, and into fake_x
+  if (lim > 2) TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, sA, 0));
+  if (lim > 3) TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, sB, setB));
+  // ---- the discriminator loss on the fakes (C: D_x(fake_x) from stream B, D: D_y(fake_y) from stream A)
+  if (overlap) { TEM_CUDA(cudaStreamWaitEvent(sC, h->ev[1], 0)); TEM_CUDA(cudaStreamWaitEvent(sD, h->ev[2], 0)); }
+  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 0.f, gamma, s_disc, lm, LS + 3, h->dlog[5], sC));
+  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 0.f, gamma, s_disc, lm, LS + 2, h->dlog[3], sD));
+  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sC, setC));
+  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sD, setD));
   if (overlap) {
     for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[6 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[6 + i], 0)); }
   }
