@@ -238,7 +238,7 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
         // shared by all four streams, so the other three must not run ahead of this pack
         (void)fresh;
         TEM_CUDA(cudaEventRecord(h->ev[11], st));
-        for (int i = 0; i < 4; ++i) if (h->aux[i] && h->aux[i] != st) TEM_CUDA(cudaStreamWaitEvent(h->aux[i], h->ev[11], 0));
+        for (int i = 0; i < 6; ++i) if (h->aux[i] && h->aux[i] != st) TEM_CUDA(cudaStreamWaitEvent(h->aux[i], h->ev[11], 0));
       }
     }
     TEM_CUDA(launch_tc_kind(kind, a, it->second.buf, st));
@@ -737,7 +737,7 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
   tem_handle* h = new tem_handle();
   h->cfg = *cfg; h->nd = cfg->is3d ? 3 : 2; h->step = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->keys_overridden = false; h->in_overlap = false; h->last_gen_net = 0; h->last_disc_net = 2; h->params_version = 1;
-  for (int i = 0; i < 4; ++i) h->aux[i] = nullptr; for (int i = 0; i < 16; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
+  for (int i = 0; i < 6; ++i) h->aux[i] = nullptr; for (int i = 0; i < 16; ++i) h->ev[i] = nullptr; h->overlap_ready = false;
   h->nets[0] = build_generator(wf, h->nd); h->nets[1] = build_generator(wf, h->nd);
   h->nets[2] = build_discriminator(wf, h->nd); h->nets[3] = build_discriminator(wf, h->nd);
   long long off = 0;
@@ -770,7 +770,15 @@ extern "C" int tem_create(const tem_config* cfg, tem_handle** out) {
       for (int i = 0; i < 11; ++i) if ((rc = alloc_tensor(h, h->gdP[sset][i], DT_BF16, B, d[i], h->nets[0].L[i].cout))) return fail(rc);
       for (int i = 0; i < 8; ++i) if ((rc = alloc_tensor(h, h->ddP[sset][i], DT_BF16, B, dd[i] > 0 ? dd[i] : 1, h->nets[2].L[i].cout))) return fail(rc);
     }
-    for (int i = 0; i < 4; ++i) if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) { tem_set_error("stream create failed"); return fail(TEM_ERR_CUDA); }
+    {
+      // the chained passes of streams A / B are the critical path of a step: their CTAs are scheduled before those of the
+      // identity / discriminator streams whenever both wait for an SM
+      int pr_lo = 0, pr_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+      static const bool no_prio = getenv("TEM_NO_STREAM_PRIORITY") != nullptr;      // debug knob
+      for (int i = 0; i < 6; ++i)
+        if (cudaStreamCreateWithPriority(&h->aux[i], cudaStreamNonBlocking, (i < 2 && !no_prio) ? pr_hi : pr_lo) != cudaSuccess) { tem_set_error("stream create failed"); return fail(TEM_ERR_CUDA); }
+    }
     for (int i = 0; i < 16; ++i) if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { tem_set_error("event create failed"); return fail(TEM_ERR_CUDA); }
     long long osz = (long long)B * h->outdim * h->outdim * (h->nd == 3 ? h->outdim : 1);
     for (int i = 0; i < 6; ++i) if ((rc = dev_alloc(h, (void**)&h->dOut[i], osz * 4))) return fail(rc);
@@ -793,7 +801,7 @@ extern "C" int tem_destroy(tem_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  for (int i = 0; i < 4; ++i) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+  for (int i = 0; i < 6; ++i) if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
   for (int i = 0; i < 16; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_tile_origins) cudaFreeHost(h->h_tile_origins);   // h_tile_index lives in the same allocation
@@ -997,12 +1005,14 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   static const char* lim_s = tem_ablation_env("TEM_DEBUG_GEN_BWD");
   const bool overlap = h->overlap_ready && !h->prof.on && !no_overlap && !lim_s;
   cudaStream_t sA = overlap ? h->aux[0] : st, sB = overlap ? h->aux[1] : st, sC = overlap ? h->aux[2] : st, sD = overlap ? h->aux[3] : st;
-  cudaStream_t ss[4] = {sA, sB, sC, sD};
+  static const bool four = getenv("TEM_FOUR_STREAMS") != nullptr;      // debug knob: discriminator passes share the identity streams
+  cudaStream_t sE = (overlap && !four) ? h->aux[4] : sC, sF = (overlap && !four) ? h->aux[5] : sD;      // E: D_x passes, F: D_y passes
+  cudaStream_t ss[6] = {sA, sB, sC, sD, sE, sF};
   const int setB = overlap ? 1 : 0, setC = overlap ? 2 : 0, setD = overlap ? 3 : 0;
   h->in_overlap = overlap;
   if (overlap) {
     TEM_CUDA(cudaEventRecord(h->ev[0], st));
-    for (int i = 0; i < 4; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
+    for (int i = 0; i < 6; ++i) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
     // Packed weight images are shared by all streams and stale after every Adam step: ~70 tiny pack launches (launch list of
     // round 2: 0.2 ms when serialised in front of the fork).  They are spread round-robin over the four streams and every
     // stream then waits for the packs of the other three.
@@ -1015,7 +1025,7 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
       }
     if (npk) {
       for (int i = 0; i < 4; ++i) TEM_CUDA(cudaEventRecord(h->ev[12 + i], ss[i]));
-      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (i != j) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[12 + j], 0));
+      for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) if (i != j) TEM_CUDA(cudaStreamWaitEvent(ss[i], h->ev[12 + j], 0));
     }
   }
   // ---- forward (pass ids: 0 fake_y, 1 cycled_x, 2 fake_x, 3 cycled_y, 4 same_x, 5 same_y)
@@ -1046,21 +1056,21 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   TEM_CHECK(gen_forward(h, F, gp[2], ry, B, n, keys + 4, sB));                         // :167
   TEM_CHECK(gen_forward(h, F, gp[4], rx, B, n, keys + 8, sC));                         // :177
   TEM_CHECK(gen_forward(h, G, gp[5], ry, B, n, keys + 10, sD));                        // :181
-  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sC));                               // :185
-  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sD));                               // :186
+  TEM_CHECK(disc_forward(h, DX, dp[0], rxc, B, od, sE));                               // :185
+  TEM_CHECK(disc_forward(h, DY, dp[1], ryc, B, od, sF));                               // :186
   TEM_CHECK(gen_forward(h, F, gp[1], fy, B, n, keys + 2, sA));                         // :162
   TEM_CHECK(gen_forward(h, G, gp[3], fx, B, n, keys + 6, sB));                         // :171
   TEM_CHECK(disc_forward(h, DX, dp[2], fxd, B, od, sB));                               // :188 (fake_x lives on stream B)
   TEM_CHECK(disc_forward(h, DY, dp[3], fyd, B, od, sA));                               // :189 (fake_y lives on stream A)
   if (overlap) { TEM_CUDA(cudaEventRecord(h->ev[1], sB)); TEM_CUDA(cudaEventRecord(h->ev[2], sA)); }
-  // ---- streams C / D: identity loss + the discriminator loss on the reals, their backward passes
+  // ---- streams C / D: identity loss and its backward pass; streams E / F: the discriminator loss on the reals
   // (loss accumulators live behind the gradient arena so one all-reduce covers both)
   TEM_CHECK(pair_loss(h, rx, (const float*)gp[4].a[11].p, B, 0, s_id, LS + 8, h->dOut[4], sC));      // identity f :200
-  TEM_CUDA(launch_focal_logits(lg_dxr, nl, 1.f, gamma, s_disc, lm, LS + 3, h->dlog[4], sC));         // disc_x :202
+  TEM_CUDA(launch_focal_logits(lg_dxr, nl, 1.f, gamma, s_disc, lm, LS + 3, h->dlog[4], sE));         // disc_x :202
   TEM_CHECK(pair_loss(h, ry, (const float*)gp[5].a[11].p, B, 0, s_id, LS + 7, h->dOut[5], sD));      // identity g :199
-  TEM_CUDA(launch_focal_logits(lg_dyr, nl, 1.f, gamma, s_disc, lm, LS + 2, h->dlog[2], sD));         // disc_y :203
-  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sC, setC));       // disc_x wrt D_x   :212
-  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sD, setD));       // disc_y wrt D_y   :214
+  TEM_CUDA(launch_focal_logits(lg_dyr, nl, 1.f, gamma, s_disc, lm, LS + 2, h->dlog[2], sF));         // disc_y :203
+  TEM_CHECK(disc_backward(h, DX, dp[0], h->dlog[4], true, nullptr, sE, setC));       // disc_x wrt D_x   :212  (the discriminator scratch of set C / D belongs to E / F)
+  TEM_CHECK(disc_backward(h, DY, dp[1], h->dlog[2], true, nullptr, sF, setD));       // disc_y wrt D_y   :214
   if (lim > 4) TEM_CHECK(gen_backward(h, F, gp[4], h->dOut[4], nullptr, sC, setC));
   if (lim > 5) TEM_CHECK(gen_backward(h, G, gp[5], h->dOut[5], nullptr, sD, setD));
   // ---- streams A / B: generator loss through the discriminator on the fake, cycle loss, their backward passes.  Stream A
@@ -1075,14 +1085,14 @@ static int train_fwd_bwd(tem_handle* h, const void* real_x, const void* real_y, 
   if (lim > 1) TEM_CHECK(gen_backward(h, G, gp[3], h->dOut[3], h->dOut[2], sB, setB));      // cycled_y -> G, and into fake_x
   if (lim > 2) TEM_CHECK(gen_backward(h, G, gp[0], h->dOut[0], nullptr, sA, 0));
   if (lim > 3) TEM_CHECK(gen_backward(h, F, gp[2], h->dOut[2], nullptr, sB, setB));
-  // ---- the discriminator loss on the fakes (C: D_x(fake_x) from stream B, D: D_y(fake_y) from stream A)
-  if (overlap) { TEM_CUDA(cudaStreamWaitEvent(sC, h->ev[1], 0)); TEM_CUDA(cudaStreamWaitEvent(sD, h->ev[2], 0)); }
-  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 0.f, gamma, s_disc, lm, LS + 3, h->dlog[5], sC));
-  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 0.f, gamma, s_disc, lm, LS + 2, h->dlog[3], sD));
-  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sC, setC));
-  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sD, setD));
+  // ---- the discriminator loss on the fakes (E: D_x(fake_x) from stream B, F: D_y(fake_y) from stream A)
+  if (overlap) { TEM_CUDA(cudaStreamWaitEvent(sE, h->ev[1], 0)); TEM_CUDA(cudaStreamWaitEvent(sF, h->ev[2], 0)); }
+  TEM_CUDA(launch_focal_logits(lg_dxf, nl, 0.f, gamma, s_disc, lm, LS + 3, h->dlog[5], sE));
+  TEM_CUDA(launch_focal_logits(lg_dyf, nl, 0.f, gamma, s_disc, lm, LS + 2, h->dlog[3], sF));
+  TEM_CHECK(disc_backward(h, DX, dp[2], h->dlog[5], true, nullptr, sE, setC));
+  TEM_CHECK(disc_backward(h, DY, dp[3], h->dlog[3], true, nullptr, sF, setD));
   if (overlap) {
-    for (int i = 0; i < 4; ++i) { TEM_CUDA(cudaEventRecord(h->ev[6 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[6 + i], 0)); }
+    for (int i = 0; i < 6; ++i) { TEM_CUDA(cudaEventRecord(h->ev[5 + i], ss[i])); TEM_CUDA(cudaStreamWaitEvent(st, h->ev[5 + i], 0)); }
   }
   h->in_overlap = false;
   h->overlap_ready = true;      // the packed-weight cache (if this model has one: 2-D models do not) is warm now

@@ -98,7 +98,7 @@ struct tem_handle {
   std::map<std::tuple<const float*, int, int>, Packed> packed;
   uint64_t params_version;
   // four internal streams overlap the independent passes of a train step (G(real_x) || F(real_y), ...)
-  cudaStream_t aux[4];
+  cudaStream_t aux[6];         // A, B: the chained generator passes (high priority: the critical path); C, D: identity passes; E, F: discriminator passes
   cudaEvent_t ev[16];
   bool overlap_ready;
   bool in_overlap;              // a train step is between its stream fork and join
