@@ -487,6 +487,172 @@ conv_down_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// DOWN, input-slice-major (second half of round 2).  conv_down_tc_kernel issues, per OUTPUT slice, one MMA per (kz, ry/rx class,
+// m'y[, m'x, channel pair]) with N = Cout padded to 16: 32 small MMAs per slice at Cin = 8, half of N padding at Cout = 8, and
+// it was MMA-issue bound (profiles/ablation_s2_r2.txt).  An input slice s feeds exactly two output slices -- zo = s/2 - 1
+// through kz = (s & 1) + 2 and zo = s/2 through kz = s & 1 -- so here the MMAs are issued per INPUT slice with
+// N = [W(kz = p + 2) | W(kz = p)] (p = s & 1) into two ADJACENT column groups of a TMEM-resident strip (group g = zo + 1):
+// half the MMAs, no padding, every ring slot is consumed by exactly one MMA group.  The strip is zeroed once (one work item
+// per CTA); output slice zo is complete when input slice 2 zo + 3 has been multiplied.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDown2MaxZ = 32;
+template <int CO, int MODE>
+__global__ void __launch_bounds__(kThreads)
+conv_down2_tc_kernel(const __grid_constant__ CUtensorMap map0, const S2Args a) {
+  constexpr int N2 = 2 * CO;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[RING_MAX], empty_bar[RING_MAX], w_bar, strip_bar, tfull_bar[kDown2MaxZ];
+  __shared__ uint32_t tmem_base_s;
+  const int RING = a.ring;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int planes = a.planes;
+  const uint32_t wbytes_pad = (uint32_t)((a.wbytes + 1023) & ~1023);
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + wbytes_pad;
+  const uint32_t slot_bytes = (uint32_t)(4 * planes) * SUB_STRIDE;
+  const uint32_t tmem_cols = (uint32_t)a.np;          // strip: (zc + 2) groups of CO columns, rounded up to a power of two
+
+  int b, x0, y0, z0, nz; decode_work(a, b, x0, y0, z0, nz);
+  const int nslices = 2 * nz + 2;                  // input slices 2*z0 - pad .. 2*(z0+nz-1) + 3 - pad
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&w_bar, 1); mbar_init(&strip_bar, 4);
+    for (int i = 0; i < nz; ++i) mbar_init(&tfull_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)a.wbytes);
+      bulk_load(wsm, a.wpacked, (uint32_t)a.wbytes, &w_bar);
+      int slot = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s) {
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        if (a.dbg & 4) { mbar_arrive(&full_bar[slot]); if (++slot == RING) { slot = 0; ph ^= 1u; } continue; }
+        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(4 * planes) * SUB_BYTES);
+        uint8_t* dst = ring + (size_t)slot * slot_bytes;
+        const int zin = 2 * z0 - a.pad + s + a.shift[0];
+        for (int rr = 0; rr < 4; ++rr) {
+          const int ry = rr >> 1, rx = rr & 1;
+          // parity r of (k - pad): k = kb, kb + 2 with kb = (r + pad) & 1; first tap offset m_lo = (kb - pad - r) / 2
+          const int mly = (((ry + a.pad) & 1) - a.pad - ry) / 2, mlx = (((rx + a.pad) & 1) - a.pad - rx) / 2;
+          const int cy = 2 * (y0 + mly) + ry + a.shift[1], cx = 2 * (x0 + mlx) + rx + a.shift[2];
+          for (int p = 0; p < planes; ++p)
+            tma_load_5d(dst + (rr * planes + p) * SUB_STRIDE, &map0, &full_bar[slot], p * 8, cx, cy, zin, b);
+        }
+        if (++slot == RING) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(&w_bar, 0);
+    const uint32_t wb16 = smem_u32(wsm) >> 4;
+    const uint32_t rbase = smem_u32(ring);
+    const uint32_t a_hi = ((uint32_t)ROW_B >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t b_lbo = ((uint32_t)(N2 * 16) >> 4) << 16;
+    const uint32_t a_lbo = a.cin8 ? (1u << 16) : (((uint32_t)SUB_STRIDE >> 4) << 16);
+    const int kcs = planes >> 1;
+    const uint32_t par16 = (uint32_t)(a.wbytes >> 1) >> 4;       // the image of input-slice parity 1 follows that of parity 0
+    mbar_wait(&strip_bar, 0);                                     // strip zeroed by the epilogue warps
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int slot = 0; uint32_t ph = 0;
+    for (int s = 0; s < nslices; ++s) {
+      mbar_wait(&full_bar[slot], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)((s >> 1) * CO);
+        const uint32_t sb16 = (rbase + (uint32_t)slot * slot_bytes) >> 4;
+        uint32_t blo = (wb16 + (uint32_t)(s & 1) * par16) | b_lbo;
+        if (!(a.dbg & 16)) {
+#pragma unroll 1
+          for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t tb16 = sb16 + (((uint32_t)(rr * planes) * SUB_STRIDE) >> 4);
+#pragma unroll
+            for (int my = 0; my < 2; ++my) {
+              if (a.cin8) {
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | ((tb16 + (uint32_t)(my * SXV)) | a_lbo), ((uint64_t)b_hi << 32) | blo, idesc, 1u);
+                blo += (uint32_t)(N2 * 32) >> 4;
+              } else {
+#pragma unroll
+                for (int mx = 0; mx < 2; ++mx) {
+                  uint32_t alo = (tb16 + (uint32_t)(my * SXV + mx)) | a_lbo;
+                  for (int kc = 0; kc < kcs; ++kc) {
+                    umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, 1u);
+                    alo += (uint32_t)(2 * SUB_STRIDE) >> 4; blo += (uint32_t)(N2 * 32) >> 4;
+                  }
+                }
+              }
+            }
+          }
+        }
+        umma_commit(&empty_bar[slot]);                           // this input slice is used by this MMA group only
+        if ((s & 1) && s >= 3) umma_commit(&tfull_bar[(s - 3) >> 1]);   // output slice (s - 3) / 2 has its four kz parts
+      }
+      __syncwarp();
+      if (++slot == RING) { slot = 0; ph ^= 1u; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, xl = row & 7;
+    const int oy = y0 + yl, ox = x0 + xl;
+    const bool inside = oy < a.L[1] && ox < a.L[2] && !(a.dbg & 1);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // zero the strip: groups 0 .. nz + 1 (group 0 and nz + 1 only collect the parts of the output slices outside this chunk)
+    for (int c = 0; c < (nz + 2) * CO; c += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(lane_base + (uint32_t)c), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (lane == 0) mbar_arrive(&strip_bar);
+    for (int zo = 0; zo < nz; ++zo) {
+      const int oz = z0 + zo;
+      uint4 refq[CO / 8], accq[CO / 8];
+      if (inside) {
+#pragma unroll
+        for (int c = 0; c < CO / 8; ++c) {
+          if (c * 8 < a.Cout) {
+            if (MODE >= 2 && a.ref) refq[c] = __ldg(reinterpret_cast<const uint4*>(a.ref + Epi::ref_off(a, b, oz, oy, ox) + c * 8));
+            if (MODE >= 2 && a.accumulate) accq[c] = *reinterpret_cast<const uint4*>(a.out + Epi::out_off(a, b, oz, oy, ox) + c * 8);
+          }
+        }
+      }
+      mbar_wait(&tfull_bar[zo], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[CO];
+      const uint32_t taddr = lane_base + (uint32_t)((zo + 1) * CO);
+#pragma unroll
+      for (int c = 0; c < CO; c += 8) tmem_ld8(taddr + c, r + c);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!inside) continue;
+#pragma unroll
+      for (int c = 0; c < CO / 8; ++c) {
+        if (c * 8 < a.Cout) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[c * 8 + u]);
+          Epi::run<MODE>(a, v, c * 8, b, oz, oy, ox, refq[c], accq[c]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // UP, wide layers (Cin multiple of 64, any Cout: wf <= 2).  Same GEMM as conv_up_tc_kernel with CP = 32 (N = 8 classes x
 // 32 output channels = 256 columns, blockIdx.y = group of 32 output channels), but K = 8 taps x Cin no longer fits in
 // shared memory as weights (Cin = 64 already needs 256 KB), so BOTH operands are streamed:
@@ -1049,7 +1215,43 @@ __global__ void pack_weights_s2_kernel(const PackS2Args a) {
   a.dst[i] = __float2bfloat16_rn(v);
 }
 
+// B image of conv_down2_tc_kernel: [input-slice parity p][ry/rx class][m'y][(m'x, channel pair)] steps of [k half][n group][8][8] with
+// N = 2 * CO columns: n < CO -> kz = p + 2, n >= CO -> kz = p
+struct PackD2Args {
+  const float* w; long long ws_tap, ws_in, ws_out;
+  int pad, cin, cols, co, cin8;
+  bf16* dst; int total;
+};
+__global__ void pack_weights_down2_kernel(const PackD2Args a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  int t = i;
+  const int e = t & 7; t >>= 3;
+  const int r = t & 7; t >>= 3;
+  const int ng = (2 * a.co) >> 3;
+  const int g = t % ng; t /= ng;
+  const int j = t & 1; t >>= 1;
+  int s = t;
+  const int n = g * 8 + r;
+  const int kcs = a.cin >> 4;
+  int mx, ci;
+  if (a.cin8) { mx = j; ci = e; }
+  else { const int kc = s % kcs; s /= kcs; mx = s & 1; s >>= 1; ci = (2 * kc + j) * 8 + e; }
+  const int my = s & 1; s >>= 1;
+  const int rr = s & 3; s >>= 2;
+  const int p = s;                                       // input-slice parity
+  const int kz = (n < a.co) ? p + 2 : p;
+  const int co = (n < a.co) ? n : n - a.co;
+  const int ry = rr >> 1, rx = rr & 1;
+  const int kby = (ry + a.pad) & 1, kbx = (rx + a.pad) & 1;      // k = kb + 2 m'
+  const int ky = kby + 2 * my, kx = kbx + 2 * mx;
+  float v = 0.f;
+  if (co < a.cols) v = a.w[(long long)((kz * 4 + ky) * 4 + kx) * a.ws_tap + (long long)ci * a.ws_in + (long long)co * a.ws_out];
+  a.dst[i] = __float2bfloat16_rn(v);
+}
+
 int cp_of(int cout) { return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32); }
+bool down2_on() { static const bool off = getenv("TEM_CONV_DOWN_V1") != nullptr; return !off; }      // debug knob: per-output-slice kernel
 int npad_of(int cout) { return cout <= 16 ? 16 : 32; }
 int steps_of(const ConvArgs& a) {
   const int cin = a.C0;
@@ -1057,6 +1259,7 @@ int steps_of(const ConvArgs& a) {
   return (a.form == 1) ? 4 * per_yz : 32 * per_yz;
 }
 size_t resident_packed_bytes(const ConvArgs& a) {
+  if (a.form != 1 && down2_on()) return (size_t)(steps_of(a) / 2) * (2 * cp_of(a.Cout)) * 32;     // conv_down2: half the steps, N = 2 * CO
   const int np = (a.form == 1) ? 8 * cp_of(a.Cout) : npad_of(a.Cout);
   return (size_t)steps_of(a) * np * 32;
 }
@@ -1123,6 +1326,13 @@ cudaError_t tc_s2_pack_weights(const ConvArgs& a, bf16* dst, cudaStream_t st) {
     PackDwArgs q; q.w = a.w; q.ws_tap = a.ws_tap; q.ws_in = a.ws_in; q.ws_out = a.ws_out;
     q.nch = a.C0 / 16; q.cout = a.Cout; q.np = dw_np(a.Cout); q.pad = a.pad[0]; q.dst = dst; q.total = (long long)(tc_s2_packed_bytes(a) / 2);
     pack_weights_dw_kernel<<<(unsigned)((q.total + 255) / 256), 256, 0, st>>>(q); ++g_tem_launches;
+    return cudaGetLastError();
+  }
+  if (a.form != 1 && down2_on()) {
+    PackD2Args q; q.w = a.w; q.ws_tap = a.ws_tap; q.ws_in = a.ws_in; q.ws_out = a.ws_out;
+    q.pad = a.pad[0]; q.cin = a.C0; q.cols = a.Cout; q.co = cp_of(a.Cout); q.cin8 = a.C0 == 8;
+    q.dst = dst; q.total = (int)(resident_packed_bytes(a) / 2);
+    pack_weights_down2_kernel<<<(q.total + 255) / 256, 256, 0, st>>>(q); ++g_tem_launches;
     return cudaGetLastError();
   }
   PackS2Args p;
@@ -1218,6 +1428,53 @@ cudaError_t launch_conv_tc_s2(const ConvArgs& a, const bf16* wpacked, cudaStream
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(conv_downw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e) return e; attr = true; }
     conv_downw_tc_kernel<<<dim3((unsigned)(cols * t.nzc), (unsigned)groups), kThreadsDw, smem, st>>>(m0, t);
+    ++g_tem_launches;
+    return cudaGetLastError();
+  }
+  if (!up && down2_on()) {
+    // input-slice-major kernel: the TMEM strip holds (zc + 2) column groups of CO columns; 256 columns keep two CTAs per SM
+    // every input slice is consumed by one MMA group: a short ring suffices, which lets more CTAs share an SM
+    const int co = cp_of(a.Cout);
+    const size_t wb2 = (resident_packed_bytes(a) + 1023) & ~(size_t)1023;
+    const size_t slot2 = (size_t)4 * (cin / 8) * SUB_STRIDE;
+    static const char* ring_s = getenv("TEM_DOWN2_RING");        // debug knob
+    t.ring = ring_s ? atoi(ring_s) : 4;
+    if (t.ring < 2) t.ring = 2; if (t.ring > RING_MAX) t.ring = RING_MAX;
+    while (t.ring > 2 && wb2 + t.ring * slot2 + 1024 > 200 * 1024) --t.ring;
+    const size_t smem2 = wb2 + t.ring * slot2 + 1024;
+    int sm_by_smem = (int)((227 * 1024) / (smem2 + 1024));
+    if (sm_by_smem > 2048 / kThreads) sm_by_smem = 2048 / kThreads;
+    if (sm_by_smem < 1) sm_by_smem = 1;
+    // z chunks: fewest waves x (input slices per chunk + a fixed cost of ~6 slices for start-up / strip zeroing / drain)
+    int zmax = 512 / co - 2;
+    if (zmax > kDown2MaxZ) zmax = kDown2MaxZ;
+    double best = 1e30; int best_nzc = (t.Q[0] + zmax - 1) / zmax;
+    for (int nzc2 = (t.Q[0] + zmax - 1) / zmax; nzc2 <= t.Q[0]; ++nzc2) {
+      const int zc2 = (t.Q[0] + nzc2 - 1) / nzc2;
+      if (zc2 < 2 && nzc2 > 1) break;
+      int tc2 = 32; while (tc2 < (zc2 + 2) * co) tc2 <<= 1;
+      int per_sm = 512 / tc2; if (per_sm > sm_by_smem) per_sm = sm_by_smem;
+      const long long ctas = cols * ((t.Q[0] + zc2 - 1) / zc2);
+      const long long waves = (ctas + 148LL * per_sm - 1) / (148LL * per_sm);
+      const double cost = (double)waves * (2 * zc2 + 2 + 6) * per_sm;      // per_sm CTAs share an SM's tensor pipe and load path
+      if (cost < best - 1e-9) { best = cost; best_nzc = nzc2; }
+    }
+    t.zc = (t.Q[0] + best_nzc - 1) / best_nzc; t.nzc = (t.Q[0] + t.zc - 1) / t.zc;
+    int tc = 32; while (tc < (t.zc + 2) * co) tc <<= 1;
+    t.np = tc;
+    if (!make_map_s2(&m0, a.s0.p, a.B, a.s0.Z, a.s0.Y, a.s0.X, a.s0.C, 2)) return cudaErrorInvalidValue;
+    const unsigned grid2 = (unsigned)(cols * t.nzc);
+    static bool attr2[12] = {};
+    const int mode2 = (!a.ref && !a.accumulate) ? (a.drop_key ? 1 : 0) : ((!a.drop_key && a.slope == 1.f) ? 2 : 3);
+#define LAUNCH_D2(COV, MD, IDX)                                                                                         \
+    {                                                                                                                   \
+      if (!attr2[IDX]) { cudaError_t e = cudaFuncSetAttribute(conv_down2_tc_kernel<COV, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; attr2[IDX] = true; } \
+      conv_down2_tc_kernel<COV, MD><<<grid2, kThreads, smem2, st>>>(m0, t);                                            \
+    }
+#define LAUNCH_D2_MODE(COV, IDX) { if (mode2 == 0) LAUNCH_D2(COV, 0, IDX) else if (mode2 == 1) LAUNCH_D2(COV, 1, IDX + 1) else if (mode2 == 2) LAUNCH_D2(COV, 2, IDX + 2) else LAUNCH_D2(COV, 3, IDX + 3) }
+    if (co == 8) LAUNCH_D2_MODE(8, 0) else if (co == 16) LAUNCH_D2_MODE(16, 4) else LAUNCH_D2_MODE(32, 8)
+#undef LAUNCH_D2_MODE
+#undef LAUNCH_D2
     ++g_tem_launches;
     return cudaGetLastError();
   }
