@@ -1,5 +1,7 @@
 """GPU parity of the full path through the reference-shaped Python API: generator / discriminator
 forward, the CycleGAN train step (losses, gradients, Adam), dropout mask injection, tiled inference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -499,3 +501,26 @@ def test_predict_ng_cube_tiling_bit_exact_and_parity():
     a = predict_ng_cube(vol, start, size, model, ms_x, ms_y, rank=0, world=2)
     b = predict_ng_cube(vol, start, size, model, ms_x, ms_y, rank=1, world=2)
     assert np.array_equal(np.maximum(a, b), out) and np.all((a == 0) | (b == 0))
+
+
+def test_concat_layer_merged_launches_match_split_launches(tmp_path):
+    """The one-launch data / weight gradients of the concat layers g10, g7 (conv_tc3.cu two-destination epilogue, wgrad_tc.cu
+    two-source tiles), the input-slice-major stride-2 kernel and the tcgen05 single-channel kernels against the launches
+    they replaced (debug knobs, read once per process): same MMAs, so gradients agree to fp32 summation order."""
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(__file__), "cat_worker.py")
+
+    def run(tag, **env):
+        out = str(tmp_path / f"{tag}.npz")
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, worker, out], check=True, env=e, timeout=600)
+        return np.load(out)
+    ref = run("merged")
+    for tag, env, tol in (("split", {"TEM_NO_DGRAD_CAT": "1", "TEM_NO_WGRAD_CAT": "1"}, 1e-5),
+                          ("down_v1", {"TEM_CONV_DOWN_V1": "1"}, 1e-5),
+                          ("c1_cuda_cores", {"TEM_NO_CONV_C1TC": "1", "TEM_NO_WGRAD_C1TC": "1"}, 1e-3)):
+        got = run(tag, **env)
+        np.testing.assert_allclose(got["losses"], ref["losses"], rtol=1e-4 if tol > 1e-4 else 1e-6, err_msg=tag)
+        for k in ("g", "f", "dx", "dy"):
+            assert rel_l2(got[k], ref[k]) < tol, (tag, k, rel_l2(got[k], ref[k]))
