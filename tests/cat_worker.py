@@ -21,14 +21,16 @@ def main():
     P = {}
     for k in NETS:
         layers = O.generator_layers(8) if k in ('g', 'f') else O.discriminator_layers(8, True)
-        P[k] = [p * 3.0 for p in O.init_params(layers, True, r)]
-    rx = r.integers(0, 256, (1, 74, 74, 74, 1), dtype=np.uint8)
-    ry = r.integers(0, 256, (1, 74, 74, 74, 1), dtype=np.uint8)
+        P[k] = [p * 2.0 for p in O.init_params(layers, True, r)]
+    # narrow uint8 range: standardised inputs within +-0.5, away from the 1/(t + 1e-7) singularity of the focal identity / cycle
+    # loss at |a - b| -> 2 (tests/test_gpu_model.py:_train_case)
+    rx = r.integers(90, 166, (1, 74, 74, 74, 1), dtype=np.uint8)
+    ry = r.integers(100, 176, (1, 74, 74, 74, 1), dtype=np.uint8)
     eng = Engine(dimsize=74, is3d=True, wf=8, max_batch=1, train=True)
     for k, net in NETS.items():
         eng.set_weights(net, P[k])
     eng.set_dropout_keys([2 * i + 101 for i in range(12)])
-    losses = eng.train_grads(rx, ry, meanstd_x=(0.02, 0.55), meanstd_y=(-0.03, 0.6))
+    losses = eng.train_grads(rx, ry, meanstd_x=(0.0, 0.6), meanstd_y=(0.08, 0.6))
     np.savez(out, losses=np.asarray(losses, np.float64), **{k: eng.get_vector(net, which=1) for k, net in NETS.items()})
     eng.close()
 

@@ -125,7 +125,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
     // the whole warp runs the issue loop convergently (uniform values stay in uniform registers); one elected lane
     // executes the MMAs / commits
     {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((3 * a.N) >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);      // N = the g rows of three consecutive g slices (dz = 2, 1, 0)
       // descriptors are affine in the start address: only the low word (start >> 4, LBO) changes inside the loops, so
       // the single issuing thread spends a couple of integer adds per MMA instead of rebuilding 64-bit descriptors
       const uint32_t lo_fixed = (128u >> 4) << 16;                                   // LBO = 128 B (next 8 voxels)
@@ -145,18 +145,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
             const uint32_t xb = sbase16 + (uint32_t)slot * slot16, gb = xb + goff16 + 2u;     // +2 voxels: the g tile starts at x = -2
             if (!(a.dbg & 16)) {
               for (int i = 0; i < n; ++i) {
-                // dz = 0, 1, 2 read g slice i+2, i+1, i of the step (zd = zx - dz)
-                const uint32_t b0 = (gb + (uint32_t)(i + 2) * gb16) | lo_fixed;
-                const uint32_t b1 = (gb + (uint32_t)(i + 1) * gb16) | lo_fixed;
-                const uint32_t b2 = (gb + (uint32_t)i * gb16) | lo_fixed;
+                // x slice i correlates with the g slices i, i+1, i+2 of the step (dz = 2, 1, 0: zd = zx - dz).  The three slices
+                // are adjacent in the slot and their rows continue each other's row stride, so ONE MMA takes all three as
+                // N = 3 * RB * Cb columns [dz = 2 | dz = 1 | dz = 0]: a third of the MMAs, three times as wide (the M = 64 x N = 48
+                // MMAs of g1 kept the tensor pipe busy 53 % of the time for 24 % of its throughput)
+                const uint32_t bg = (gb + (uint32_t)i * gb16) | lo_fixed;
                 uint32_t alo = (xb + (uint32_t)i * xa16) | lo_fixed;
                 for (int r = 0; r < a.NR; ++r) {
                   const uint32_t ro = (uint32_t)r * 16u;           // 16 voxels = 256 B = 16 descriptor units
                   const uint64_t ad = ((uint64_t)a_hi << 32) | alo;
-#define WT_MMA(ACC, BLO) umma_bf16(tmem_base + (ACC) * N, ad, ((uint64_t)b_hi << 32) | (BLO), idesc, acc)
-                  WT_MMA(0, b0 + ro); WT_MMA(1, b0 + ro - 1u); WT_MMA(2, b0 + ro - 2u);
-                  WT_MMA(3, b1 + ro); WT_MMA(4, b1 + ro - 1u); WT_MMA(5, b1 + ro - 2u);
-                  WT_MMA(6, b2 + ro); WT_MMA(7, b2 + ro - 1u); WT_MMA(8, b2 + ro - 2u);
+#define WT_MMA(DX, BLO) umma_bf16(tmem_base + (DX) * 3u * N, ad, ((uint64_t)b_hi << 32) | (BLO), idesc, acc)
+                  WT_MMA(0, bg + ro); WT_MMA(1, bg + ro - 1u); WT_MMA(2, bg + ro - 2u);
 #undef WT_MMA
                   alo += 16u; acc = 1u;
                 }
@@ -203,8 +202,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant_
         float* rowp = red + ((size_t)((dz * 3 + ty) * 3 + dx) * Ca + ca) * CbP;
         for (int pB = 0; pB < a.pb; pB += 2) {              // two 8-column loads in flight per wait
           uint32_t r[16];
-          tmem_ld8(lane_base + (uint32_t)(acc * a.N + (pB * a.RB + j) * 8), r);
-          if (pB + 1 < a.pb) tmem_ld8(lane_base + (uint32_t)(acc * a.N + ((pB + 1) * a.RB + j) * 8), r + 8);
+          const uint32_t cbase = (uint32_t)((dx * 3 + (2 - dz)) * a.N);          // accumulator dx, column block of g slice 2 - dz
+          tmem_ld8(lane_base + cbase + (uint32_t)((pB * a.RB + j) * 8), r);
+          if (pB + 1 < a.pb) tmem_ld8(lane_base + cbase + (uint32_t)(((pB + 1) * a.RB + j) * 8), r + 8);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (use) {
 #pragma unroll
