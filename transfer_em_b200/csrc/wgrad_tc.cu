@@ -275,7 +275,10 @@ bool plan(const WgradArgs& w, WtArgs& t, size_t& smem) {
   // pipeline step: sb x-slices with >= ~64 MMAs between two hand-overs (at least 2: a step re-loads two g slices);
   // as many slots as ~150 KB allow (one CTA per SM anyway: the accumulators take most of TMEM), at least two
   static const char* sb_s = getenv("TEM_WTC_SB");        // debug knob
+  // (measured, profiles/negative_results_r2.md: the loads run at ~2.7 TB/s from L2 whatever the request granularity, so what counts is
+  // the (sb + 2) / sb re-read factor of g: four slices per step took g1 from 64.7 to 58.2 us, g10 from 49.9 to 41.5)
   int sb = sb_s ? atoi(sb_s) : (64 + 9 * t.NR - 1) / (9 * t.NR);
+  if (!sb_s && sb < 4) sb = 4;
   if (sb < 2) sb = 2; if (sb > 6) sb = 6;
   auto slot_of = [&](int n) { return (size_t)n * t.xa_bytes + (size_t)(n + 2) * t.gb_bytes; };
   while (sb > 1 && 2 * slot_of(sb) > 180 * 1024) --sb;
