@@ -17,12 +17,6 @@ namespace {
 constexpr int TZ = 4, TY = 8, TXT = 32;
 constexpr int HZc = TZ + 2, HYc = TY + 2, HXc = TXT + 2;
 
-__device__ __forceinline__ float ld1(const SrcView& S, long long off, const float* lut) {
-  if (S.dtype == DT_U8) return lut[reinterpret_cast<const uint8_t*>(S.p)[off]];
-  if (S.dtype == DT_BF16) return bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
-  return reinterpret_cast<const float*>(S.p)[off];
-}
-
 template <int CO>
 __global__ void __launch_bounds__(256) conv_c1in_kernel(const ConvArgs a, const int ntx, const int nty, const int ntz, const int flip) {
   __shared__ float lut[256];

@@ -223,12 +223,10 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
     }
     auto key = std::make_tuple(a.w, a.form, a.Cout);
     auto it = h->packed.find(key);
-    bool fresh = false;
     if (it == h->packed.end()) {
       tem_handle::Packed p; p.bytes = bytes; p.version = ~0ull; p.buf = nullptr; p.args = a; p.kind = kind;
       TEM_CHECK(dev_alloc(h, (void**)&p.buf, bytes));
       it = h->packed.emplace(key, p).first;
-      fresh = true;
     }
     if (it->second.version != h->params_version) {
       TEM_CUDA(pack_tc_weights(kind, a, it->second.buf, st));
@@ -236,7 +234,6 @@ static int dispatch_conv(const tem_handle* hc, ConvArgs& a, cudaStream_t st) {
       if (h->in_overlap) {
         // a key first seen inside an overlapped step (e.g. a larger batch selects another kernel variant): the image is
         // shared by all four streams, so the other three must not run ahead of this pack
-        (void)fresh;
         TEM_CUDA(cudaEventRecord(h->ev[11], st));
         for (int i = 0; i < 6; ++i) if (h->aux[i] && h->aux[i] != st) TEM_CUDA(cudaStreamWaitEvent(h->aux[i], h->ev[11], 0));
       }

@@ -12,12 +12,6 @@ static const char* g_wgrad_c1_name = "wgrad_c1_kernel";    // kernel family the 
 
 namespace {
 
-__device__ __forceinline__ float load1(const SrcView& S, long long off, const float* lut) {
-  if (S.dtype == DT_U8) return lut[reinterpret_cast<const uint8_t*>(S.p)[off]];
-  if (S.dtype == DT_BF16) return bf2f(reinterpret_cast<const bf16*>(S.p)[off]);
-  return reinterpret_cast<const float*>(S.p)[off];
-}
-
 constexpr int WZ = 4, WY = 8, WX = 32;                 // positions per tile; 256 threads = 32 x 8, 4 z-positions each
 constexpr int HZw = WZ + 2, HYw = WY + 2, HXw = WX + 2;
 

@@ -49,10 +49,6 @@ struct Wc1Args {
   int dbg;                     // stage-ablation bits (-DTEM_ABLATION builds only): 2 no atomics, 4 no s gather, 8 no P copies, 16 no MMAs
 };
 
-__device__ __forceinline__ uint64_t wc_desc_mn(uint32_t saddr16, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // SWIZZLE_NONE MN-major: LBO between 8-row K groups, SBO between 8-element MN groups
-  return (uint64_t)(saddr16 & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
 __device__ __forceinline__ void wc_tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
@@ -232,7 +228,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_c1tc_kernel(const Wc1Args
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int slot = m >> 3, c8 = m & 7;
+    const int slot = m >> 3;                                 // lane = slot * 8 + channel of the group
     const int jz = (ncg == 2) ? (slot & 7) : slot;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     // a warp holds four plane slots of one channel group (lane = slot_in_warp * 8 + c8): shuffles add them up (a shared-memory

@@ -52,12 +52,6 @@ struct WtArgs {
   int dbg;                     // stage-ablation bits (-DTEM_ABLATION builds only): 1 no epilogue, 2 no atomics, 4 no x loads, 8 no g loads, 16 no MMAs
 };
 
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // SWIZZLE_NONE MN-major: ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16 B units - SBO between 8-channel groups, LBO between 8-voxel K groups
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapx1, const __grid_constant__ CUtensorMap mapg, const WtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
